@@ -1,0 +1,587 @@
+// Memory-bound glue kernels of the Point-SAM hot path (LayerNorm family, SwiGLU, mini-PointNet first
+// layer, group max-pool, softmax, positional encoding, small attention, upsampling, mask product).
+// Each kernel cites the reference op it replaces in include/psam_b200.h.
+#include "psam_common.cuh"
+#include "../../include/psam_b200.h"
+
+namespace psam {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ void store_split(__nv_bfloat16* hi, long long plane, long long off, float v) {
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[off] = h;
+    hi[off + plane] = l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm (one warp per row; two-pass mean/variance like F.layer_norm)
+// ---------------------------------------------------------------------------------------------
+__global__ void layernorm_kernel(const psam_ln_args a) {
+    const int warps_per_block = blockDim.x >> 5;
+    const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= a.rows) return;
+    const float* x = a.x + row * a.ldx;
+    const float* r = a.r ? a.r + row * a.ldr : nullptr;
+    const float* gb = a.gbias ? a.gbias + (row / a.group_rows) * a.ld_gbias : nullptr;
+    auto val = [&](int c) {
+        float v = x[c];
+        if (r) v += r[c];
+        if (gb) v += gb[c];
+        return v;
+    };
+    float s = 0.f;
+    for (int c = lane; c < a.D; c += 32) s += val(c);
+    const float mean = warp_sum(s) / (float)a.D;
+    float q = 0.f;
+    for (int c = lane; c < a.D; c += 32) {
+        const float d = val(c) - mean;
+        q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)a.D + a.eps);
+    __nv_bfloat16* yh = (__nv_bfloat16*)a.y_hi;
+    for (int c = lane; c < a.D; c += 32) {
+        float v = (val(c) - mean) * rstd * a.gamma[c] + a.beta[c];
+        v = apply_act(v, a.act);
+        if (a.y) a.y[row * a.ldy + c] = v;
+        if (yh) store_split(yh, a.y_plane, row * a.ldy_s + c, v);
+    }
+    if (yh)
+        for (int c = a.D + lane; c < a.pitch; c += 32) {
+            yh[row * a.ldy_s + c] = __float2bfloat16_rn(0.f);
+            yh[row * a.ldy_s + c + a.y_plane] = __float2bfloat16_rn(0.f);
+        }
+}
+
+__global__ void swiglu_ln_kernel(const float* __restrict__ gx, long long ld, long long x_off, int rows, int H,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 __nv_bfloat16* __restrict__ yh, long long y_plane, long long ldy_s, long long pitch) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* g = gx + row * ld;
+    const float* x = g + x_off;
+    auto val = [&](int c) { return silu(g[c]) * x[c]; };
+    float s = 0.f;
+    for (int c = lane; c < H; c += 32) s += val(c);
+    const float mean = warp_sum(s) / (float)H;
+    float q = 0.f;
+    for (int c = lane; c < H; c += 32) {
+        const float d = val(c) - mean;
+        q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+    for (int c = lane; c < H; c += 32) store_split(yh, y_plane, row * ldy_s + c, (val(c) - mean) * rstd * gamma[c] + beta[c]);
+    for (int c = H + lane; c < pitch; c += 32) {
+        yh[row * ldy_s + c] = __float2bfloat16_rn(0.f);
+        yh[row * ldy_s + c + y_plane] = __float2bfloat16_rn(0.f);
+    }
+}
+
+// y = act(LN?(x W^T + b)); Cin <= 8; one warp per row, lane owns outputs lane, lane+32, ...
+template <int CPL>  // outputs per lane = Cout / 32
+__global__ void small_in_linear_kernel(const float* __restrict__ x, int rows, int Cin, const float* __restrict__ W,
+                                       const float* __restrict__ b, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, int use_ln, int act,
+                                       __nv_bfloat16* __restrict__ yh, long long y_plane, long long ldy_s) {
+    extern __shared__ float s_w[];  // [Cout*Cin] + [Cout] bias
+    const int Cout = CPL * 32;
+    for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) s_w[i] = W[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_w[Cout * Cin + i] = b ? b[i] : 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+        float xin[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) xin[c] = c < Cin ? x[row * Cin + c] : 0.f;
+        float o[CPL];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const int n = lane + 32 * i;
+            float acc = s_w[Cout * Cin + n];
+            for (int c = 0; c < Cin; ++c) acc = fmaf(xin[c], s_w[n * Cin + c], acc);
+            o[i] = acc;
+            s += acc;
+        }
+        if (use_ln) {
+            const float mean = warp_sum(s) / (float)Cout;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) q += (o[i] - mean) * (o[i] - mean);
+            const float rstd = rsqrtf(warp_sum(q) / (float)Cout + eps);
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) o[i] = (o[i] - mean) * rstd * gamma[lane + 32 * i] + beta[lane + 32 * i];
+        }
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) store_split(yh, y_plane, row * ldy_s + lane + 32 * i, apply_act(o[i], act));
+    }
+}
+
+__global__ void group_max_kernel(const float* __restrict__ x, long long ldx, int groups, int K, int D, float* __restrict__ y,
+                                 long long ldy, __nv_bfloat16* __restrict__ yh, long long y_plane, long long ldy_s) {
+    const int g = blockIdx.x;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        const float* p = x + (long long)g * K * ldx + c;
+        float m = p[0];
+        for (int k = 1; k < K; ++k) m = fmaxf(m, p[(long long)k * ldx]);
+        if (y) y[(long long)g * ldy + c] = m;
+        if (yh) store_split(yh, y_plane, (long long)g * ldy_s + c, m);
+    }
+}
+
+__global__ void softmax_split_kernel(const float* __restrict__ s, long long lds, long long rows, int L, float scale,
+                                     __nv_bfloat16* __restrict__ ph, long long p_plane, long long ldp) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* x = s + row * lds;
+    float m = -3.4e38f;
+    for (int c = lane; c < L; c += 32) m = fmaxf(m, x[c] * scale);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int c = lane; c < L; c += 32) sum += __expf(x[c] * scale - m);
+    const float inv = 1.0f / warp_sum(sum);
+    for (int c = lane; c < L; c += 32) store_split(ph, p_plane, row * ldp + c, __expf(x[c] * scale - m) * inv);
+}
+
+__global__ void transpose_split_kernel(const __nv_bfloat16* __restrict__ src, long long src_plane, long long src_ld,
+                                       long long src_z1, long long src_z2, __nv_bfloat16* __restrict__ dst,
+                                       long long dst_plane, long long dst_ld, long long dst_z1, long long dst_z2, int rows,
+                                       int cols, int nz1) {
+    __shared__ __nv_bfloat16 tile[2][32][34];
+    const int z = blockIdx.z, z1 = z % nz1, z2 = z / nz1;
+    src += z1 * src_z1 + z2 * src_z2;
+    dst += z1 * dst_z1 + z2 * dst_z2;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) {
+            tile[0][i][threadIdx.x] = src[(long long)r * src_ld + c];
+            tile[1][i][threadIdx.x] = src[(long long)r * src_ld + c + src_plane];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) {
+            dst[(long long)c * dst_ld + r] = tile[0][threadIdx.x][i];
+            dst[(long long)c * dst_ld + r + dst_plane] = tile[1][threadIdx.x][i];
+        }
+    }
+}
+
+__global__ void posenc_kernel(const float* __restrict__ coords, long long rows, const float* __restrict__ gauss, int F,
+                              const int* __restrict__ labels, const float* __restrict__ emb0, const float* __restrict__ emb1,
+                              float* __restrict__ out, int* __restrict__ bad_flag) {
+    const long long row = blockIdx.x;
+    if (row >= rows) return;
+    const float x = coords[row * 3], y = coords[row * 3 + 1], z = coords[row * 3 + 2];
+    if (threadIdx.x == 0 && bad_flag) {
+        const float lo = -1.0f - 1e-6f, hi = 1.0f + 1e-6f;
+        if (x < lo || y < lo || z < lo || x > hi || y > hi || z > hi) *bad_flag = 1;
+    }
+    const float* emb = nullptr;
+    if (labels) {
+        const int l = labels[row];
+        emb = l == 0 ? emb0 : (l == 1 ? emb1 : nullptr);
+    }
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        // coords @ G accumulates x*g0 + y*g1 + z*g2 in that order, then * 2*pi (prompt_encoder.py:30-32)
+        float t = x * gauss[f];
+        t = fmaf(y, gauss[F + f], t);
+        t = fmaf(z, gauss[2 * F + f], t);
+        t *= 6.283185307179586f;
+        float sv, cv;
+        sincosf(t, &sv, &cv);
+        if (emb) {
+            sv += emb[f];
+            cv += emb[F + f];
+        }
+        out[row * 2 * F + f] = sv;
+        out[row * 2 * F + F + f] = cv;
+    }
+}
+
+// one warp per (z, head, query); scores kept in shared memory (Lk <= 4096)
+__global__ void attention_small_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                       float* __restrict__ o, int Z, int Lq, int Lk, int H, int dh, long long ldq, long long ldk,
+                                       long long ldv, long long ldo) {
+    extern __shared__ float s_sc[];  // [warps][Lk] + [warps][dh] query
+    const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * wpb + w;
+    if (item >= (long long)Z * H * Lq) return;
+    const int i = (int)(item % Lq);
+    const int h = (int)((item / Lq) % H);
+    const int z = (int)(item / ((long long)Lq * H));
+    float* sc = s_sc + (size_t)w * (Lk + dh);
+    float* sq = sc + Lk;
+    const float* qp = q + ((long long)z * Lq + i) * ldq + h * dh;
+    for (int d = lane; d < dh; d += 32) sq[d] = qp[d];
+    __syncwarp();
+    const float scale = rsqrtf((float)dh);
+    float m = -3.4e38f;
+    for (int j = lane; j < Lk; j += 32) {
+        const float* kp = k + ((long long)z * Lk + j) * ldk + h * dh;
+        float acc = 0.f;
+        for (int d = 0; d < dh; ++d) acc = fmaf(sq[d], kp[d], acc);
+        acc *= scale;
+        sc[j] = acc;
+        m = fmaxf(m, acc);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < Lk; j += 32) {
+        const float e = __expf(sc[j] - m);
+        sc[j] = e;
+        sum += e;
+    }
+    const float inv = 1.0f / warp_sum(sum);
+    __syncwarp();
+    float* op = o + ((long long)z * Lq + i) * ldo + h * dh;
+    for (int d = lane; d < dh; d += 32) {
+        float acc = 0.f;
+        for (int j = 0; j < Lk; ++j) acc = fmaf(sc[j], v[((long long)z * Lk + j) * ldv + h * dh + d], acc);
+        op[d] = acc * inv;
+    }
+}
+
+__global__ void decoder_prepare_kernel(const float* __restrict__ iou_token, const float* __restrict__ mask_tokens, int nmt,
+                                       const float* __restrict__ sparse, int P, const float* __restrict__ pc_emb,
+                                       const float* __restrict__ dense, long long dense_z, long long dense_g, int Z, int rep,
+                                       int G, int D, float* __restrict__ tokens, float* __restrict__ src) {
+    const int T = 1 + nmt + P;
+    const long long n_tok = (long long)Z * T * D, n_src = (long long)Z * G * D;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_tok + n_src; i += (long long)gridDim.x * blockDim.x) {
+        if (i < n_tok) {
+            const int d = (int)(i % D);
+            const int t = (int)((i / D) % T);
+            const int z = (int)(i / ((long long)D * T));
+            float v;
+            if (t == 0) v = iou_token[d];
+            else if (t <= nmt) v = mask_tokens[(t - 1) * D + d];
+            else v = sparse[((long long)z * P + (t - 1 - nmt)) * D + d];
+            tokens[i] = v;
+        } else {
+            const long long j = i - n_tok;
+            const int d = (int)(j % D);
+            const int g = (int)((j / D) % G);
+            const int z = (int)(j / ((long long)D * G));
+            src[j] = pc_emb[((long long)(z / rep) * G + g) * D + d] + dense[z * dense_z + g * dense_g + d];
+        }
+    }
+}
+
+// one warp per point; D <= 1024 (D/32 values per lane)
+__global__ void interp_ln_gelu_kernel(const float* __restrict__ f, int Z, int rep, int G, int D, const long long* __restrict__ idx,
+                                      const float* __restrict__ w, int N, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ yh, long long y_plane,
+                                      long long ldy_s) {
+    const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+    const long long total = (long long)Z * N;
+    for (long long pt = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); pt < total; pt += (long long)gridDim.x * wpb) {
+        const int z = (int)(pt / N);
+        const int n = (int)(pt % N);
+        const long long o3 = ((long long)(z / rep) * N + n) * 3;
+        const float w0 = w[o3], w1 = w[o3 + 1], w2 = w[o3 + 2];
+        const float* f0 = f + ((long long)z * G + idx[o3]) * D;
+        const float* f1 = f + ((long long)z * G + idx[o3 + 1]) * D;
+        const float* f2 = f + ((long long)z * G + idx[o3 + 2]) * D;
+        float vals[32];
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            const int c = lane + 32 * t;
+            float v = 0.f;
+            if (c < D) v = (f0[c] * w0 + f1[c] * w1) + f2[c] * w2;
+            vals[t] = v;
+            s += v;
+        }
+        const float mean = warp_sum(s) / (float)D;
+        float q = 0.f;
+#pragma unroll
+        for (int t = 0; t < 32; ++t)
+            if (lane + 32 * t < D) q += (vals[t] - mean) * (vals[t] - mean);
+        const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            const int c = lane + 32 * t;
+            if (c < D) store_split(yh, y_plane, pt * ldy_s + c, gelu_erf((vals[t] - mean) * rstd * gamma[c] + beta[c]));
+        }
+    }
+}
+
+__global__ void mask_dot_kernel(const float* __restrict__ u, long long ldu, const float* __restrict__ hyper, int Z, int C, int N,
+                                int D, float* __restrict__ masks) {
+    extern __shared__ float s_h[];  // [C*D] for this z
+    const int z = blockIdx.y;
+    for (int i = threadIdx.x; i < C * D; i += blockDim.x) s_h[i] = hyper[(long long)z * C * D + i];
+    __syncthreads();
+    const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
+    for (int n = blockIdx.x * wpb + (threadIdx.x >> 5); n < N; n += gridDim.x * wpb) {
+        const float* up = u + ((long long)z * N + n) * ldu;
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float x = up[d];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (c < C) acc[c] = fmaf(x, s_h[c * D + d], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c < C) {
+                const float r = warp_sum(acc[c]);
+                if (lane == 0) masks[((long long)z * C + c) * N + n] = r;
+            }
+    }
+}
+
+__global__ void add_bcast_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, long long chunk,
+                                 long long rep, long long period, float* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long bi = ((i / chunk) / rep) * chunk + (i % chunk);
+        out[i] = a[i] + b[bi % period];
+    }
+}
+
+__global__ void split_f32_kernel(const float* __restrict__ x, long long ld, long long rows, int D, __nv_bfloat16* __restrict__ yh,
+                                 long long y_plane, long long ldy_s, long long pitch) {
+    const long long total = rows * pitch;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / pitch;
+        const int c = (int)(i % pitch);
+        store_split(yh, y_plane, r * ldy_s + c, c < D ? x[r * ld + c] : 0.f);
+    }
+}
+
+// fp32 SIMT linear: 64x64 tile, 256 threads, 4x4 per thread
+__global__ void __launch_bounds__(256) linear_f32_kernel(const psam_linear_args a) {
+    __shared__ float sx[16][65];
+    __shared__ float sw[16][65];
+    const int z = blockIdx.z;
+    const float* x = a.x + z * a.x_z;
+    const float* x2 = a.x2 ? a.x2 + z * a.x2_z : nullptr;
+    const float* w = a.w + z * a.w_z;
+    const float* b = a.b ? a.b + z * a.b_z : nullptr;
+    const float* r = a.r ? a.r + z * a.r_z : nullptr;
+    float* y = a.y + z * a.y_z;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < a.K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int rr = i >> 4, kk = i & 15;
+            const int m = m0 + rr, n = n0 + rr, k = k0 + kk;
+            float xv = 0.f, wv = 0.f;
+            if (k < a.K) {
+                if (m < a.M) {
+                    xv = x[(long long)m * a.ldx + k];
+                    if (x2) xv += x2[(long long)m * a.ldx + k];
+                }
+                if (n < a.N) wv = w[(long long)n * a.ldw + k];
+            }
+            sx[kk][rr] = xv;
+            sw[kk][rr] = wv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float xa[4], wb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xa[i] = sx[kk][ty * 4 + i], wb[i] = sw[kk][tx * 4 + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], wb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+            if (m < a.M && n < a.N) {
+                float v = acc[i][j];
+                if (b) v += b[n];
+                v = apply_act(v, a.act);
+                if (r) v += r[(long long)m * a.ldy + n];
+                y[(long long)m * a.ldy + n] = v;
+            }
+        }
+}
+
+static inline int grid_for(long long work, int per_block, int max_blocks = 148 * 32) {
+    long long g = (work + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+}  // namespace psam
+
+using namespace psam;
+
+extern "C" int psam_layernorm_f32(const psam_ln_args* a, cudaStream_t stream) {
+    if (!a || !a->x || !a->gamma || !a->beta || a->rows <= 0 || a->D <= 0 || (!a->y && !a->y_hi)) return PSAM_ERR_ARG;
+    if (a->gbias && a->group_rows <= 0) return PSAM_ERR_ARG;
+    layernorm_kernel<<<ceil_div(a->rows, 8), 256, 0, stream>>>(*a);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_swiglu_ln(const float* gx, long long ld, long long x_off, int rows, int H, const float* gamma,
+                              const float* beta, float eps, void* y_hi, long long y_plane, long long ldy_s, long long pitch,
+                              cudaStream_t stream) {
+    if (!gx || !gamma || !beta || !y_hi || rows <= 0 || H <= 0 || pitch < H) return PSAM_ERR_ARG;
+    swiglu_ln_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(gx, ld, x_off, rows, H, gamma, beta, eps, (__nv_bfloat16*)y_hi,
+                                                            y_plane, ldy_s, pitch);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_small_in_linear(const float* x, int rows, int Cin, const float* W, const float* b, const float* gamma,
+                                    const float* beta, float eps, int use_ln, int act, int Cout, void* y_hi,
+                                    long long y_plane, long long ldy_s, cudaStream_t stream) {
+    if (!x || !W || !y_hi || rows <= 0 || Cin <= 0 || Cin > 8 || Cout % 32 || Cout <= 0 || Cout > 512) return PSAM_ERR_ARG;
+    if (use_ln && (!gamma || !beta)) return PSAM_ERR_ARG;
+    const size_t smem = (size_t)(Cout * Cin + Cout) * sizeof(float);
+    const int blocks = grid_for(rows, 8, 148 * 8);
+    __nv_bfloat16* yh = (__nv_bfloat16*)y_hi;
+#define PSAM_SIL(CPL)                                                                                                     \
+    small_in_linear_kernel<CPL><<<blocks, 256, smem, stream>>>(x, rows, Cin, W, b, gamma, beta, eps, use_ln, act, yh, \
+                                                                 y_plane, ldy_s)
+    switch (Cout / 32) {
+        case 1: PSAM_SIL(1); break;
+        case 2: PSAM_SIL(2); break;
+        case 4: PSAM_SIL(4); break;
+        case 8: PSAM_SIL(8); break;
+        case 16: PSAM_SIL(16); break;
+        default: return PSAM_ERR_UNSUPPORTED;
+    }
+#undef PSAM_SIL
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_group_max(const float* x, long long ldx, int groups, int K, int D, float* y, long long ldy, void* y_hi,
+                              long long y_plane, long long ldy_s, cudaStream_t stream) {
+    if (!x || groups <= 0 || K <= 0 || D <= 0 || (!y && !y_hi)) return PSAM_ERR_ARG;
+    group_max_kernel<<<groups, 256, 0, stream>>>(x, ldx, groups, K, D, y, ldy, (__nv_bfloat16*)y_hi, y_plane, ldy_s);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_softmax_split(const float* s, long long lds, long long rows, int L, float scale, void* p_hi,
+                                  long long p_plane, long long ldp, cudaStream_t stream) {
+    if (!s || !p_hi || rows <= 0 || L <= 0) return PSAM_ERR_ARG;
+    softmax_split_kernel<<<(unsigned)ceil_div_ll(rows, 8), 256, 0, stream>>>(s, lds, rows, L, scale, (__nv_bfloat16*)p_hi, p_plane, ldp);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_transpose_split(const void* src_hi, long long src_plane, long long src_ld, long long src_z1,
+                                    long long src_z2, void* dst_hi, long long dst_plane, long long dst_ld, long long dst_z1,
+                                    long long dst_z2, int rows, int cols, int nz1, int nz2, cudaStream_t stream) {
+    if (!src_hi || !dst_hi || rows <= 0 || cols <= 0 || nz1 <= 0 || nz2 <= 0) return PSAM_ERR_ARG;
+    dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), nz1 * nz2);
+    transpose_split_kernel<<<grid, dim3(32, 8), 0, stream>>>((const __nv_bfloat16*)src_hi, src_plane, src_ld, src_z1, src_z2,
+                                                             (__nv_bfloat16*)dst_hi, dst_plane, dst_ld, dst_z1, dst_z2, rows,
+                                                             cols, nz1);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_posenc_f32(const float* coords, long long rows, const float* gauss, int F, const int* labels,
+                               const float* emb0, const float* emb1, float* out, int* bad_flag, cudaStream_t stream) {
+    if (!coords || !gauss || !out || rows <= 0 || F <= 0) return PSAM_ERR_ARG;
+    if (labels && (!emb0 || !emb1)) return PSAM_ERR_ARG;
+    posenc_kernel<<<(unsigned)rows, 128, 0, stream>>>(coords, rows, gauss, F, labels, emb0, emb1, out, bad_flag);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_attention_f32(const float* q, const float* k, const float* v, float* o, int Z, int Lq, int Lk, int H,
+                                  int dh, long long ldq, long long ldk, long long ldv, long long ldo, cudaStream_t stream) {
+    if (!q || !k || !v || !o || Z <= 0 || Lq <= 0 || Lk <= 0 || H <= 0 || dh <= 0) return PSAM_ERR_ARG;
+    const int wpb = 4;
+    const size_t smem = (size_t)wpb * (Lk + dh) * sizeof(float);
+    if (smem > 200 * 1024) return PSAM_ERR_UNSUPPORTED;
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long items = (long long)Z * H * Lq;
+    attention_small_kernel<<<(unsigned)ceil_div_ll(items, wpb), wpb * 32, smem, stream>>>(q, k, v, o, Z, Lq, Lk, H, dh, ldq, ldk,
+                                                                                         ldv, ldo);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_decoder_prepare(const float* iou_token, const float* mask_tokens, int n_mask_tokens, const float* sparse,
+                                    int P, const float* pc_emb, const float* dense, long long dense_z, long long dense_g, int Z,
+                                    int rep, int G, int D, float* tokens, float* src, cudaStream_t stream) {
+    if (!iou_token || !mask_tokens || !pc_emb || !dense || !tokens || !src || Z <= 0 || rep <= 0 || (P > 0 && !sparse)) return PSAM_ERR_ARG;
+    const long long total = (long long)Z * (1 + n_mask_tokens + P) * D + (long long)Z * G * D;
+    decoder_prepare_kernel<<<grid_for(total, 256), 256, 0, stream>>>(iou_token, mask_tokens, n_mask_tokens, sparse, P, pc_emb,
+                                                                     dense, dense_z, dense_g, Z, rep, G, D, tokens, src);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_interp_ln_gelu(const float* f, int Z, int rep, int G, int D, const long long* idx, const float* w, int N,
+                                   const float* gamma, const float* beta, float eps, void* y_hi, long long y_plane,
+                                   long long ldy_s, cudaStream_t stream) {
+    if (!f || !idx || !w || !gamma || !beta || !y_hi || Z <= 0 || rep <= 0 || D <= 0 || D > 1024) return PSAM_ERR_ARG;
+    interp_ln_gelu_kernel<<<grid_for((long long)Z * N, 8), 256, 0, stream>>>(f, Z, rep, G, D, idx, w, N, gamma, beta, eps,
+                                                                             (__nv_bfloat16*)y_hi, y_plane, ldy_s);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_mask_dot(const float* u, long long ldu, const float* hyper, int Z, int C, int N, int D, float* masks,
+                             cudaStream_t stream) {
+    if (!u || !hyper || !masks || Z <= 0 || C <= 0 || C > 8 || N <= 0 || D <= 0) return PSAM_ERR_ARG;
+    const size_t smem = (size_t)C * D * sizeof(float);
+    dim3 grid(grid_for(N, 8, 148 * 8), Z);
+    mask_dot_kernel<<<grid, 256, smem, stream>>>(u, ldu, hyper, Z, C, N, D, masks);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_add_bcast_f32(const float* a, const float* b, long long n, long long chunk, long long rep,
+                                  long long b_period, float* out, cudaStream_t stream) {
+    if (!a || !b || !out || n <= 0 || b_period <= 0 || chunk <= 0 || rep <= 0) return PSAM_ERR_ARG;
+    add_bcast_kernel<<<grid_for(n, 256), 256, 0, stream>>>(a, b, n, chunk, rep, b_period, out);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_split_f32(const float* x, long long ld, long long rows, int D, void* y_hi, long long y_plane,
+                              long long ldy_s, long long pitch, cudaStream_t stream) {
+    if (!x || !y_hi || rows <= 0 || D <= 0 || pitch < D) return PSAM_ERR_ARG;
+    split_f32_kernel<<<grid_for(rows * pitch, 256), 256, 0, stream>>>(x, ld, rows, D, (__nv_bfloat16*)y_hi, y_plane, ldy_s, pitch);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_linear_f32(const psam_linear_args* a, cudaStream_t stream) {
+    if (!a || !a->x || !a->w || !a->y || a->M <= 0 || a->N <= 0 || a->K <= 0 || a->Z <= 0) return PSAM_ERR_ARG;
+    dim3 grid(ceil_div(a->N, 64), ceil_div(a->M, 64), a->Z);
+    linear_f32_kernel<<<grid, 256, 0, stream>>>(*a);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" const char* psam_version(void) { return "psam_b200 0.1 (sm_100a)"; }

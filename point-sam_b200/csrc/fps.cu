@@ -1,0 +1,264 @@
+// Farthest-point sampling for sm_100a.
+//
+// Replaces torkit3d's sample_farthest_points_cuda
+// (third_party/torkit3d/torkit3d/csrc/cuda/sample_farthest_points_kernel.cu:8-165) and the
+// batch_index_select of the centres that follows it (pc_sam/model/common.py:91-92).
+//
+// Design: one thread-block CLUSTER per cloud.  The cloud (xyz + running min-distance) lives in the
+// registers of the cluster's threads for the whole kernel, so an iteration touches no global memory.
+// Per iteration every warp reduces its candidates with redux.sync, publishes one 20-byte record
+// (max-distance bits, tie-break priority, xyz of the candidate) into the shared memory of EVERY CTA
+// of the cluster (DSMEM store) and signals that CTA's mbarrier (remote arrive, release.cluster); all
+// threads then wait on their local mbarrier (acquire.cluster) and reduce the C*W records.  There is
+// no __syncthreads and no barrier.cluster in the loop - one DSMEM hop per iteration.
+//
+// Bit-exactness: squared distance is fmaf(dz,dz,fmaf(dy,dy,dx*dx)) with d = p_j - p_sel, and among
+// equal maxima the winner is the lexicographic minimum of (bitrev(j mod T), j div T), T = the
+// reference's block size for this N; if the maximum is 0 the previous index
+// is repeated.  Independent of how points are distributed over threads here.
+#include "psam_common.cuh"
+#include "../../include/psam_b200.h"
+
+namespace psam {
+
+constexpr int FPS_THREADS = 256;
+constexpr int FPS_WARPS = FPS_THREADS / 32;
+constexpr int FPS_MAX_CLUSTER = 16;
+constexpr int FPS_MAX_SLOTS = FPS_MAX_CLUSTER * FPS_WARPS;
+
+__device__ __forceinline__ uint32_t fps_prio(uint32_t j, uint32_t tmask, int log2T) {
+    // smaller is better: bit-reversed (j mod T) in the top log2T bits, (j div T) below.
+    return __brev(j & tmask) | (j >> log2T);
+}
+
+__device__ __forceinline__ float fps_sqdist(float x, float y, float z, float cx, float cy, float cz) {
+    const float dx = __fsub_rn(x, cx), dy = __fsub_rn(y, cy), dz = __fsub_rn(z, cz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// PPT > 0: register-resident points (PPT per thread).  PPT == 0: streaming fallback for clouds that
+// exceed the register capacity of a cluster; min-distance then lives in the global workspace `ws`.
+template <int PPT>
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long long* __restrict__ idx_out,
+                   float* __restrict__ centers_out, float* __restrict__ ws) {
+    __shared__ __align__(16) uint4 slot_a[2][FPS_MAX_SLOTS];  // {dist bits, prio, x, y}
+    __shared__ float slot_z[2][FPS_MAX_SLOTS];
+    __shared__ __align__(8) uint64_t mbar[2];
+
+    const uint32_t C = cluster_nctarank();
+    const uint32_t rank = cluster_ctarank();
+    const int cloud = blockIdx.x / C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nslots = C * FPS_WARPS;
+    const uint32_t tmask = (1u << log2T) - 1u;
+    const uint32_t qmask = (log2T == 32) ? 0u : ((1u << (32 - log2T)) - 1u);
+    const int stride = (int)C * FPS_THREADS;
+    const int gt = (int)rank * FPS_THREADS + tid;
+
+    xyz += (size_t)cloud * N * 3;
+    idx_out += (size_t)cloud * G;
+    centers_out += (size_t)cloud * G * 3;
+    float* md_g = (PPT == 0) ? ws + (size_t)cloud * N : nullptr;
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&mbar[0]), nslots);
+        mbar_init(smem_u32(&mbar[1]), nslots);
+        fence_mbar_init();
+    }
+
+    float px[PPT > 0 ? PPT : 1], py[PPT > 0 ? PPT : 1], pz[PPT > 0 ? PPT : 1], md[PPT > 0 ? PPT : 1];
+    if constexpr (PPT > 0) {
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            const int j = s * stride + gt;
+            if (j < N) {
+                px[s] = xyz[(size_t)j * 3 + 0];
+                py[s] = xyz[(size_t)j * 3 + 1];
+                pz[s] = xyz[(size_t)j * 3 + 2];
+                md[s] = __int_as_float(0x7f800000);  // +inf
+            } else {
+                px[s] = py[s] = pz[s] = 0.0f;
+                md[s] = 0.0f;  // never a candidate unless everything is 0 (then the result is ignored)
+            }
+        }
+    } else {
+        for (int j = gt; j < N; j += stride) md_g[j] = __int_as_float(0x7f800000);
+    }
+
+    float cx = xyz[0], cy = xyz[1], cz = xyz[2];
+    uint32_t sel = 0;
+    if (rank == 0 && tid == 0) {
+        idx_out[0] = 0;
+        centers_out[0] = cx;
+        centers_out[1] = cy;
+        centers_out[2] = cz;
+    }
+    cluster_sync_all();  // barriers initialised everywhere before the first remote arrive
+
+    for (int it = 1; it < G; ++it) {
+        const int p = it & 1;
+        // ---- 1. update min-distances, per-thread maximum -------------------------------------
+        float best = 0.0f;
+        uint32_t myprio = 0xFFFFFFFFu;
+        float wx = 0.f, wy = 0.f, wz = 0.f;
+        if constexpr (PPT > 0) {
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) {
+                const float d = fps_sqdist(px[s], py[s], pz[s], cx, cy, cz);
+                md[s] = fminf(md[s], d);
+                best = fmaxf(best, md[s]);
+            }
+        } else {
+            for (int j = gt; j < N; j += stride) {
+                const float x = xyz[(size_t)j * 3], y = xyz[(size_t)j * 3 + 1], z = xyz[(size_t)j * 3 + 2];
+                const float m = fminf(md_g[j], fps_sqdist(x, y, z, cx, cy, cz));
+                md_g[j] = m;
+                const uint32_t pr = fps_prio((uint32_t)j, tmask, log2T);
+                if (m > best || (m == best && pr < myprio)) {
+                    best = m;
+                    myprio = pr;
+                    wx = x, wy = y, wz = z;
+                }
+            }
+        }
+        // ---- 2. warp candidate: max distance, then min priority ------------------------------
+        const uint32_t bestbits = __float_as_uint(best);
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, bestbits);
+        if constexpr (PPT > 0) {
+            if (bestbits == wmax) {
+#pragma unroll
+                for (int s = 0; s < PPT; ++s) {
+                    const uint32_t pr = fps_prio((uint32_t)(s * stride + gt), tmask, log2T);
+                    if (__float_as_uint(md[s]) == wmax && pr < myprio) {
+                        myprio = pr;
+                        wx = px[s], wy = py[s], wz = pz[s];
+                    }
+                }
+            }
+        } else {
+            if (bestbits != wmax) myprio = 0xFFFFFFFFu;
+        }
+        const uint32_t wprio = __reduce_min_sync(0xffffffffu, myprio);
+        const uint32_t owner_mask = __ballot_sync(0xffffffffu, myprio == wprio && bestbits == wmax);
+        const int owner = __ffs(owner_mask) - 1;
+        const float ox = __shfl_sync(0xffffffffu, wx, owner);
+        const float oy = __shfl_sync(0xffffffffu, wy, owner);
+        const float oz = __shfl_sync(0xffffffffu, wz, owner);
+        // ---- 3. publish to every CTA of the cluster (lane c serves peer c) --------------------
+        if ((uint32_t)lane < C) {
+            const uint32_t slot = rank * FPS_WARPS + warp;
+            const uint32_t ra = mapa_shared(smem_u32(&slot_a[p][slot]), lane);
+            const uint32_t rz = mapa_shared(smem_u32(&slot_z[p][slot]), lane);
+            const uint32_t rb = mapa_shared(smem_u32(&mbar[p]), lane);
+            st_cluster_v4(ra, wmax, wprio, __float_as_uint(ox), __float_as_uint(oy));
+            st_cluster_u32(rz, __float_as_uint(oz));
+            mbar_arrive_remote_release(rb);
+        }
+        // ---- 4. wait for all C*W records of this iteration ------------------------------------
+        {
+            const uint32_t bar = smem_u32(&mbar[p]);
+            const uint32_t parity = ((uint32_t)(it - 1) >> 1) & 1u;
+            while (!mbar_try_wait_acquire_cluster(bar, parity)) {
+            }
+        }
+        // ---- 5. reduce the records (every warp redundantly) -----------------------------------
+        uint32_t gbits = 0, gprio = 0xFFFFFFFFu;
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        for (uint32_t s = lane; s < nslots; s += 32) {
+            const uint4 a = slot_a[p][s];
+            const float z = slot_z[p][s];
+            if (a.x > gbits || (a.x == gbits && a.y < gprio)) {
+                gbits = a.x;
+                gprio = a.y;
+                gx = __uint_as_float(a.z);
+                gy = __uint_as_float(a.w);
+                gz = z;
+            }
+        }
+        const uint32_t fmax = __reduce_max_sync(0xffffffffu, gbits);
+        const uint32_t fprio = __reduce_min_sync(0xffffffffu, gbits == fmax ? gprio : 0xFFFFFFFFu);
+        const uint32_t fmask = __ballot_sync(0xffffffffu, gbits == fmax && gprio == fprio);
+        const int fo = __ffs(fmask) - 1;
+        const float nx = __shfl_sync(0xffffffffu, gx, fo);
+        const float ny = __shfl_sync(0xffffffffu, gy, fo);
+        const float nz = __shfl_sync(0xffffffffu, gz, fo);
+        if (fmax != 0u) {  // max == 0: every remaining point coincides with a selected one -> repeat
+            cx = nx, cy = ny, cz = nz;
+            sel = ((fprio & qmask) << log2T) | (__brev(fprio & ~qmask));
+        }
+        if (rank == 0 && tid == 0) {
+            idx_out[it] = (long long)sel;
+            centers_out[it * 3 + 0] = cx;
+            centers_out[it * 3 + 1] = cy;
+            centers_out[it * 3 + 2] = cz;
+        }
+    }
+    cluster_sync_all();  // no CTA may exit while peers can still write into its shared memory
+}
+
+template <int PPT>
+static int launch_fps(const float* xyz, int B, int N, int G, int log2T, long long* idx, float* centers, float* ws,
+                      int cluster, cudaStream_t stream) {
+    auto kern = fps_cluster_kernel<PPT>;
+    if (cluster > 8) PSAM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * cluster));
+    cfg.blockDim = dim3(FPS_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PSAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, N, G, log2T, idx, centers, ws));
+    return PSAM_OK;
+}
+
+static void fps_plan(int N, int max_cluster, int* cluster, int* ppt) {
+    // Prefer the largest cluster (least work per SM), then the smallest PPT that holds the cloud.
+    int c = max_cluster;
+    while (c > 1 && (c / 2) * FPS_THREADS >= N) c /= 2;
+    long long per_thread = ceil_div_ll(N, (long long)c * FPS_THREADS);
+    int p = 1;
+    while (p < per_thread) p *= 2;
+    *cluster = c;
+    *ppt = (p <= 32) ? p : 0;
+}
+
+}  // namespace psam
+
+extern "C" size_t psam_fps_workspace_bytes(int B, int N, int G) {
+    (void)G;
+    int cluster, ppt;
+    psam::fps_plan(N, 8, &cluster, &ppt);
+    return ppt == 0 ? (size_t)B * N * sizeof(float) : 0;
+}
+
+extern "C" int psam_fps_f32(const float* xyz, int B, int N, int G, long long* idx_out, float* centers_out,
+                            void* workspace, cudaStream_t stream) {
+    using namespace psam;
+    if (!xyz || !idx_out || !centers_out || B <= 0 || N <= 0 || G <= 0 || G > N) return PSAM_ERR_ARG;
+    // reference block size: smallest power of two >= N capped at 512, floor 32 (utils.h:13-19, :153-161)
+    int T = 1;
+    while (T < N && T < 512) T *= 2;
+    if (T < 64) T = 32;
+    int log2T = 0;
+    while ((1 << log2T) < T) ++log2T;
+    int cluster, ppt;
+    fps_plan(N, 8, &cluster, &ppt);
+    if (ppt == 0 && !workspace) return PSAM_ERR_ARG;
+    float* ws = (float*)workspace;
+    switch (ppt) {
+        case 1: return launch_fps<1>(xyz, B, N, G, log2T, idx_out, centers_out, ws, cluster, stream);
+        case 2: return launch_fps<2>(xyz, B, N, G, log2T, idx_out, centers_out, ws, cluster, stream);
+        case 4: return launch_fps<4>(xyz, B, N, G, log2T, idx_out, centers_out, ws, cluster, stream);
+        case 8: return launch_fps<8>(xyz, B, N, G, log2T, idx_out, centers_out, ws, cluster, stream);
+        case 16: return launch_fps<16>(xyz, B, N, G, log2T, idx_out, centers_out, ws, cluster, stream);
+        case 32: return launch_fps<32>(xyz, B, N, G, log2T, idx_out, centers_out, ws, cluster, stream);
+        default: return launch_fps<0>(xyz, B, N, G, log2T, idx_out, centers_out, ws, cluster, stream);
+    }
+}

@@ -1,0 +1,383 @@
+// kNN grouping and 3-NN interpolation weights for sm_100a.
+//
+// Replaces pc_sam/model/common.py: knn_points (:27-56, torch.cdist + torch.topk), the gathers of
+// KNNGrouper.forward / group_with_centers_and_knn (:99-123, :126-187) and compute_interp_weights
+// (:238-255).  The reference materialises the [B,G,N] distance matrix (64 MiB per cloud at
+// G=512,N=32768); here nothing but xyz is read and only the K winners are written.
+//
+// psam_knn_f32: one CTA per query centre.
+//   A. squared distances to a strided SAMPLE of the keys -> shared memory; exact K-th smallest of the
+//      sample by bitwise bisection -> tau, an upper bound of the true K-th distance.
+//   B. one pass over ALL keys (xyz streamed from L2), candidates with d2 <= tau appended to a
+//      shared-memory list (warp-aggregated).  Expected size ~K*stride; if the list overflows
+//      (adversarial duplicates) the kernel falls back to exact bisection over the whole key set.
+//   C. exact K-th among the candidates by bisection; ties at the K-th distance resolved by lower key
+//      index; output sorted by (distance, index) so the result is deterministic.
+// Distances are the direct-difference form fmaf(dz,dz,fmaf(dy,dy,dx*dx)) (exact for coincident points).
+#include "psam_common.cuh"
+#include "../../include/psam_b200.h"
+
+namespace psam {
+
+constexpr int KNN_THREADS = 256;
+constexpr int KNN_MAX_CAP = 16384;     // candidate list capacity limit
+constexpr int KNN_MAX_SAMPLE = 16384;  // sample distances kept in shared memory
+
+__device__ __forceinline__ float sqdist3(float x, float y, float z, float cx, float cy, float cz) {
+    const float dx = x - cx, dy = y - cy, dz = z - cz;
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// Block-wide sum of per-thread counts through one shared counter slot (one __syncthreads).
+__device__ __forceinline__ int block_count(int c, int* slot) {
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(slot, c);
+    __syncthreads();
+    return *slot;
+}
+
+// Bit pattern of the k-th smallest (1-indexed) of vals[0..n) (non-negative floats compared as
+// unsigned).  cnt[0..31) must be zero on entry and is left dirty.
+__device__ uint32_t kth_smallest_smem(const float* vals, int n, int k, int* cnt) {
+    uint32_t res = 0;
+    for (int bit = 30; bit >= 0; --bit) {
+        const uint32_t cand = res | (1u << bit);
+        int c = 0;
+        for (int i = threadIdx.x; i < n; i += KNN_THREADS) c += (__float_as_uint(vals[i]) < cand);
+        if (block_count(c, &cnt[bit]) < k) res = cand;
+    }
+    return res;
+}
+
+__device__ __forceinline__ void zero_counters(int* cnt) {
+    __syncthreads();
+    if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_kernel(const float* __restrict__ query, const float* __restrict__ key, int Q, int N, int K, int sample_stride,
+           int sample_cap, int cap, long long* __restrict__ idx_out, float* __restrict__ d2_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_sample = reinterpret_cast<float*>(smem_raw);  // [sample_cap] (>= 2K); reused as the final list
+    float* c_d2 = s_sample + sample_cap;                   // [cap]
+    int* c_idx = reinterpret_cast<int*>(c_d2 + cap);       // [cap]
+    int* cnt = c_idx + cap;                                // [64]
+    __shared__ int s_ncand, s_overflow, s_nsel;
+    __shared__ int s_wcnt[KNN_THREADS / 32];
+
+    const int b = blockIdx.y, q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    key += (size_t)b * N * 3;
+    const float* pq = query + ((size_t)b * Q + q) * 3;
+    const float cx = pq[0], cy = pq[1], cz = pq[2];
+
+    if (tid == 0) s_ncand = 0, s_overflow = 0, s_nsel = 0;
+    zero_counters(cnt);
+
+    // ---- A. sample bound ---------------------------------------------------------------------
+    const int ns = (N + sample_stride - 1) / sample_stride;
+    for (int i = tid; i < ns; i += KNN_THREADS) {
+        const size_t j = (size_t)i * sample_stride;
+        s_sample[i] = sqdist3(key[j * 3], key[j * 3 + 1], key[j * 3 + 2], cx, cy, cz);
+    }
+    __syncthreads();
+    uint32_t tau = kth_smallest_smem(s_sample, ns, K, cnt);
+    zero_counters(cnt);
+
+    // ---- B. collect candidates d2 <= tau -------------------------------------------------------
+    for (int j0 = 0; j0 < N; j0 += KNN_THREADS) {
+        const int j = j0 + tid;
+        float d = 0.f;
+        bool hit = false;
+        if (j < N) {
+            d = sqdist3(key[(size_t)j * 3], key[(size_t)j * 3 + 1], key[(size_t)j * 3 + 2], cx, cy, cz);
+            hit = __float_as_uint(d) <= tau;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_ncand, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit) {
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                if (pos < cap) {
+                    c_d2[pos] = d;
+                    c_idx[pos] = j;
+                } else {
+                    s_overflow = 1;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    int ncand = s_ncand;
+    if (s_overflow) {
+        // ---- fallback: exact bisection over the whole key set (distances recomputed per pass) ----
+        uint32_t res = 0;
+        for (int bit = 30; bit >= 0; --bit) {
+            const uint32_t cand = res | (1u << bit);
+            int c = 0;
+            for (int j = tid; j < N; j += KNN_THREADS)
+                c += (__float_as_uint(sqdist3(key[(size_t)j * 3], key[(size_t)j * 3 + 1], key[(size_t)j * 3 + 2], cx, cy, cz)) < cand);
+            if (block_count(c, &cnt[bit]) < K) res = cand;
+        }
+        zero_counters(cnt);
+        if (tid == 0) s_ncand = 0;
+        __syncthreads();
+        tau = res;  // the exact K-th distance
+        // strictly-below first (fewer than K of them), then ties in ascending key index until full
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int j0 = 0; j0 < N; j0 += KNN_THREADS) {
+                const int j = j0 + tid;
+                float d = 0.f;
+                bool hit = false;
+                if (j < N) {
+                    d = sqdist3(key[(size_t)j * 3], key[(size_t)j * 3 + 1], key[(size_t)j * 3 + 2], cx, cy, cz);
+                    const uint32_t u = __float_as_uint(d);
+                    hit = pass == 0 ? (u < tau) : (u == tau);
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) s_wcnt[tid >> 5] = __popc(m);
+                __syncthreads();
+                int base = s_ncand;
+                for (int w = 0; w < (tid >> 5); ++w) base += s_wcnt[w];
+                if (hit) {
+                    const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (pos < cap) {
+                        c_d2[pos] = d;
+                        c_idx[pos] = j;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int tot = 0;
+                    for (int w = 0; w < KNN_THREADS / 32; ++w) tot += s_wcnt[w];
+                    s_ncand = min(s_ncand + tot, cap);
+                }
+                __syncthreads();
+                if (s_ncand >= cap) break;
+            }
+        }
+        ncand = s_ncand;
+    }
+
+    // ---- C. exact K-th among candidates; ties at the K-th distance by lower key index -----------
+    const uint32_t kth = kth_smallest_smem(c_d2, ncand, K, cnt);
+    zero_counters(cnt);
+    int c_lt = 0, c_le = 0;
+    for (int i = tid; i < ncand; i += KNN_THREADS) {
+        const uint32_t u = __float_as_uint(c_d2[i]);
+        c_lt += (u < kth);
+        c_le += (u <= kth);
+    }
+    c_lt = block_count(c_lt, &cnt[32]);
+    c_le = block_count(c_le, &cnt[33]);
+    uint32_t idx_thr = 0xFFFFFFFFu;  // keep ties with index <= idx_thr
+    if (c_le > K) {
+        const int need = K - c_lt;  // >= 1
+        uint32_t res = 0;           // `need`-th smallest index among the ties
+        for (int bit = 30; bit >= 0; --bit) {
+            const uint32_t cand = res | (1u << bit);
+            int c = 0;
+            for (int i = tid; i < ncand; i += KNN_THREADS)
+                c += (__float_as_uint(c_d2[i]) == kth && (uint32_t)c_idx[i] < cand);
+            if (block_count(c, &cnt[bit]) < need) res = cand;
+        }
+        idx_thr = res;
+    }
+    __syncthreads();
+    // compact the K winners into the (now free) sample area, then order them by (d2, index)
+    float* f_d2 = s_sample;
+    int* f_idx = reinterpret_cast<int*>(s_sample + K);
+    for (int i0 = 0; i0 < ncand; i0 += KNN_THREADS) {
+        const int i = i0 + tid;
+        bool hit = false;
+        if (i < ncand) {
+            const uint32_t u = __float_as_uint(c_d2[i]);
+            hit = (u < kth) || (u == kth && (uint32_t)c_idx[i] <= idx_thr);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nsel, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit) {
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                if (pos < K) {
+                    f_d2[pos] = c_d2[i];
+                    f_idx[pos] = c_idx[i];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < K; i += KNN_THREADS) {
+        const uint32_t u = __float_as_uint(f_d2[i]);
+        const int ji = f_idx[i];
+        int rank = 0;
+        for (int t = 0; t < K; ++t) {
+            const uint32_t ut = __float_as_uint(f_d2[t]);
+            rank += (ut < u) || (ut == u && f_idx[t] < ji);
+        }
+        idx_out[((size_t)b * Q + q) * K + rank] = ji;
+        if (d2_out) d2_out[((size_t)b * Q + q) * K + rank] = f_d2[i];
+    }
+}
+
+// groups[b2, g, k, :] = [ (xyz[b, idx] - centers[b, g]) / radius , feats[b2, idx, 0:C] ]  (b = b2 / rep)
+__global__ void group_gather_kernel(const float* __restrict__ xyz, const float* __restrict__ feats,
+                                    const float* __restrict__ centers, const long long* __restrict__ knn_idx, int B2,
+                                    int rep, int N, int G, int K, int C, float inv_radius, float* __restrict__ out) {
+    const long long total = (long long)B2 * G * K;
+    const int CO = 3 + C;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
+        const int b2 = (int)(r / ((long long)G * K));
+        const int g = (int)((r / K) % G);
+        const int k = (int)(r % K);
+        const int b = b2 / rep;
+        const long long j = knn_idx[((size_t)b * G + g) * K + k];
+        const float* p = xyz + ((size_t)b * N + j) * 3;
+        const float* c = centers + ((size_t)b * G + g) * 3;
+        float* o = out + (size_t)r * CO;
+        o[0] = (p[0] - c[0]) * inv_radius;
+        o[1] = (p[1] - c[1]) * inv_radius;
+        o[2] = (p[2] - c[2]) * inv_radius;
+        const float* f = feats + ((size_t)b2 * N + j) * C;
+        for (int ch = 0; ch < C; ++ch) o[3 + ch] = f[ch];
+    }
+}
+
+// 3 nearest centres per point + inverse-squared-distance weights (common.py:238-255).
+__global__ void __launch_bounds__(256)
+knn3_interp_kernel(const float* __restrict__ xyz, const float* __restrict__ centers, int N, int G,
+                   long long* __restrict__ idx_out, float* __restrict__ w_out) {
+    extern __shared__ float s_c[];  // [G*3]
+    const int b = blockIdx.y;
+    centers += (size_t)b * G * 3;
+    for (int i = threadIdx.x; i < G * 3; i += blockDim.x) s_c[i] = centers[i];
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float* p = xyz + ((size_t)b * N + n) * 3;
+    const float x = p[0], y = p[1], z = p[2];
+    float d0 = 3.4e38f, d1 = 3.4e38f, d2 = 3.4e38f;
+    int i0 = 0, i1 = 0, i2 = 0;
+    for (int g = 0; g < G; ++g) {
+        const float d = sqdist3(s_c[g * 3], s_c[g * 3 + 1], s_c[g * 3 + 2], x, y, z);
+        if (d < d2) {
+            if (d < d1) {
+                d2 = d1, i2 = i1;
+                if (d < d0) {
+                    d1 = d0, i1 = i0;
+                    d0 = d, i0 = g;
+                } else {
+                    d1 = d, i1 = g;
+                }
+            } else {
+                d2 = d, i2 = g;
+            }
+        }
+    }
+    // reference: dist = cdist (sqrt), then dist.square(), clamp(min=1e-8), reciprocal, normalise
+    const float e0 = sqrtf(d0), e1 = sqrtf(d1), e2 = sqrtf(d2);
+    const float v0 = 1.0f / fmaxf(e0 * e0, 1e-8f), v1 = 1.0f / fmaxf(e1 * e1, 1e-8f), v2 = 1.0f / fmaxf(e2 * e2, 1e-8f);
+    const float s = (v0 + v1) + v2;
+    const size_t o = ((size_t)b * N + n) * 3;
+    idx_out[o] = i0, idx_out[o + 1] = i1, idx_out[o + 2] = i2;
+    w_out[o] = v0 / s, w_out[o + 1] = v1 / s, w_out[o + 2] = v2 / s;
+}
+
+
+// Nearest-neighbour squared distance of every query to a key set (brute force, key tiles in smem).
+// Replaces chamfer_distance_forward (torkit3d csrc/cuda/chamfer_distance_kernel.cu:10-89) as used by
+// sample_furthest_points_from_border (pc_sam/model/common.py:466): dist1 and idx1 only.
+__global__ void __launch_bounds__(256)
+nn_distance_kernel(const float* __restrict__ q, const float* __restrict__ key, int n1, int n2, float* __restrict__ dist,
+                   long long* __restrict__ idx) {
+    __shared__ float s_k[256 * 3];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (i < n1) x = q[(size_t)i * 3], y = q[(size_t)i * 3 + 1], z = q[(size_t)i * 3 + 2];
+    float best = 3.4e38f;
+    int bi = -1;
+    for (int j0 = 0; j0 < n2; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        if (j < n2) {
+            s_k[threadIdx.x * 3] = key[(size_t)j * 3];
+            s_k[threadIdx.x * 3 + 1] = key[(size_t)j * 3 + 1];
+            s_k[threadIdx.x * 3 + 2] = key[(size_t)j * 3 + 2];
+        }
+        __syncthreads();
+        const int lim = min(256, n2 - j0);
+        for (int t = 0; t < lim; ++t) {
+            const float d = sqdist3(s_k[t * 3], s_k[t * 3 + 1], s_k[t * 3 + 2], x, y, z);
+            if (d < best) best = d, bi = j0 + t;
+        }
+        __syncthreads();
+    }
+    if (i < n1) {
+        dist[i] = best;
+        if (idx) idx[i] = bi;
+    }
+}
+
+}  // namespace psam
+
+extern "C" int psam_nn_distance_f32(const float* query, const float* key, int n1, int n2, float* dist_out,
+                                    long long* idx_out, cudaStream_t stream) {
+    using namespace psam;
+    if (!query || !key || !dist_out || n1 <= 0 || n2 <= 0) return PSAM_ERR_ARG;
+    nn_distance_kernel<<<ceil_div(n1, 256), 256, 0, stream>>>(query, key, n1, n2, dist_out, idx_out);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_knn_f32(const float* query, const float* key, int B, int Q, int N, int K, long long* idx_out,
+                            float* d2_out, cudaStream_t stream) {
+    using namespace psam;
+    if (!query || !key || !idx_out || B <= 0 || Q <= 0 || N <= 0 || K <= 0 || K > N) return PSAM_ERR_ARG;
+    if (K > 1024) return PSAM_ERR_UNSUPPORTED;
+    // sample stride: expected candidate count ~ K*stride (<= 1024), sample size >= 4K and <= the smem limit
+    int stride = 1;
+    while ((long long)K * stride * 2 <= 1024 && (N + 2 * stride - 1) / (2 * stride) >= 4 * K) stride *= 2;
+    while ((N + stride - 1) / stride > KNN_MAX_SAMPLE) stride *= 2;
+    const int ns = (N + stride - 1) / stride;
+    int sample_cap = ns > 2 * K ? ns : 2 * K;
+    sample_cap = (sample_cap + 3) & ~3;
+    long long cap = (long long)4 * K * stride;
+    if (cap < 1024) cap = 1024;
+    if (cap > KNN_MAX_CAP) cap = KNN_MAX_CAP;
+    if (cap > N) cap = (N + 3) & ~3;  // cannot hold more candidates than keys
+    if (cap < K) return PSAM_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)sample_cap * 4 + (size_t)cap * 8 + 64 * 4;
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_kernel<<<dim3(Q, B), KNN_THREADS, smem, stream>>>(query, key, Q, N, K, stride, sample_cap, (int)cap, idx_out, d2_out);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_group_gather_f32(const float* xyz, const float* feats, const float* centers,
+                                     const long long* knn_idx, int B, int rep, int N, int G, int K, int C, float radius,
+                                     float* groups_out, cudaStream_t stream) {
+    using namespace psam;
+    if (!xyz || !feats || !centers || !knn_idx || !groups_out || B <= 0 || rep <= 0 || C < 0) return PSAM_ERR_ARG;
+    const long long total = (long long)B * rep * G * K;
+    const int blocks = (int)min((long long)148 * 16, ceil_div_ll(total, 256));
+    group_gather_kernel<<<blocks, 256, 0, stream>>>(xyz, feats, centers, knn_idx, B * rep, rep, N, G, K, C,
+                                                    radius > 0.f ? 1.0f / radius : 1.0f, groups_out);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_knn3_interp_f32(const float* xyz, const float* centers, int B, int N, int G, long long* idx_out,
+                                    float* w_out, cudaStream_t stream) {
+    using namespace psam;
+    if (!xyz || !centers || !idx_out || !w_out || B <= 0 || N <= 0 || G < 3) return PSAM_ERR_ARG;
+    const size_t smem = (size_t)G * 3 * sizeof(float);
+    if (smem > 200 * 1024) return PSAM_ERR_UNSUPPORTED;
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(knn3_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn3_interp_kernel<<<dim3(ceil_div(N, 256), B), 256, smem, stream>>>(xyz, centers, N, G, idx_out, w_out);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}

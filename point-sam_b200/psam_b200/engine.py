@@ -1,0 +1,441 @@
+"""Execution engine: runs the Point-SAM hot path through the C ABI kernels.
+
+The modules in ``pc_sam.model`` only hold parameters (reference state-dict layout); their ``forward``
+methods call the ``run_*`` functions here.  Weights are re-packed (split-bf16, fused qkv, padded SwiGLU)
+lazily and cached per module; the cache is keyed on parameter storage/version so ``load_state_dict``,
+``safetensors.load_model`` and ``.cuda()`` are picked up automatically.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import native as nv
+from . import ops
+from .ops import ACT_GELU, ACT_NONE, ACT_RELU, Split
+
+PASSES = 3  # split-bf16 (fp32-parity) mode; 1 = plain bf16 (fails the 1e-3 parity bound)
+
+
+def _fingerprint(module) -> tuple:
+    return tuple((p.data_ptr(), p._version) for p in module.parameters()) + tuple(
+        (b.data_ptr(), b._version) for b in module.buffers())
+
+
+def _cached(module, builder):
+    fp = _fingerprint(module)
+    c = module.__dict__.get("_psam_packed")
+    if c is None or c[0] != fp:
+        if any(not p.is_cuda for p in module.parameters()):
+            raise RuntimeError("psam_b200: model parameters must live on a CUDA device (no CPU path)")
+        c = (fp, builder(module))
+        module.__dict__["_psam_packed"] = c
+    return c[1]
+
+
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+def _split_k_for(M: int, N: int, K: int) -> int:
+    """Fill the 148 SMs when the output has few tiles (small-batch inference)."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    kb = (K + 63) // 64
+    s = 1
+    while tiles * s * 2 <= 148 and s * 2 <= max(1, kb // 4):
+        s *= 2
+    return s
+
+
+# ------------------------------------------------------------------------------------------------
+# PatchEncoder (mini-PointNet), pc_sam/model/common.py:477-506
+# ------------------------------------------------------------------------------------------------
+class _PackedPatchEncoder:
+    def __init__(self, m):
+        c1, c2 = m.conv1, m.conv2
+        self.h0 = c1[0].out_features
+        self.h1 = c2[0].out_features
+        self.cout = c2[3].out_features
+        self.w10, self.b10 = _f32(c1[0].weight), _f32(c1[0].bias)
+        self.g11, self.be11, self.eps11 = _f32(c1[1].weight), _f32(c1[1].bias), c1[1].eps
+        self.w13, self.b13 = ops.pack_weight(c1[3].weight), _f32(c1[3].bias)
+        w20 = c2[0].weight.detach().float()
+        self.w20a = ops.pack_weight(w20[:, : self.h0])  # acts on the pooled (broadcast) half
+        self.w20b = ops.pack_weight(w20[:, self.h0:])   # acts on the per-point half
+        self.b20 = _f32(c2[0].bias)
+        self.g21, self.be21, self.eps21 = _f32(c2[1].weight), _f32(c2[1].bias), c2[1].eps
+        self.w23, self.b23 = ops.pack_weight(c2[3].weight), _f32(c2[3].bias)
+
+
+def run_patch_encoder(m, patches: torch.Tensor, want_split: bool = False):
+    """patches [B,L,K,Cin] fp32 -> [B,L,Cout] fp32 (and optionally the split-bf16 copy)."""
+    pk = _cached(m, _PackedPatchEncoder)
+    B, L, K, Cin = patches.shape
+    dev = patches.device
+    R, BG = B * L * K, B * L
+    h1 = Split(R, pk.h0, dev)
+    ops.small_in_linear(patches, pk.w10, pk.b10, pk.g11, pk.be11, pk.eps11, True, ACT_GELU, h1)
+    x1 = torch.empty((R, pk.h0), dtype=torch.float32, device=dev)
+    x1s = Split(R, pk.h0, dev)
+    ops.gemm(h1, pk.w13, bias=pk.b13, out_f32=x1, out_split=x1s, passes=PASSES)
+    y1s = Split(BG, pk.h0, dev)
+    ops.group_max(x1, BG, K, out_split=y1s)
+    # conv2[0] on cat([max, x]) = W_a max + W_b x + b : the pooled half is computed once per group
+    t = torch.empty((BG, pk.h1), dtype=torch.float32, device=dev)
+    ops.gemm(y1s, pk.w20a, bias=pk.b20, out_f32=t, passes=PASSES)
+    x2 = torch.empty((R, pk.h1), dtype=torch.float32, device=dev)
+    ops.gemm(x1s, pk.w20b, out_f32=x2, passes=PASSES)
+    h2 = Split(R, pk.h1, dev)
+    ops.layernorm(x2, pk.g21, pk.be21, pk.eps21, gbias=t, group_rows=K, act=ACT_GELU, out_split=h2)
+    x3 = torch.empty((R, pk.cout), dtype=torch.float32, device=dev)
+    ops.gemm(h2, pk.w23, bias=pk.b23, out_f32=x3, passes=PASSES)
+    emb = torch.empty((B, L, pk.cout), dtype=torch.float32, device=dev)
+    embs = Split(BG, pk.cout, dev) if want_split else None
+    ops.group_max(x3, BG, K, out_f32=emb, out_split=embs)
+    return (emb, embs) if want_split else emb
+
+
+# ------------------------------------------------------------------------------------------------
+# KNNGrouper, pc_sam/model/common.py:59-123
+# ------------------------------------------------------------------------------------------------
+def run_knn_grouper(g, xyz, features, use_fps=True):
+    if not use_fps:
+        raise NotImplementedError("use_fps=False is only used by the hierarchical variant (out of scope)")
+    xyz32 = xyz.float().contiguous()
+    feats = features.float().contiguous()
+    B, N, _ = xyz32.shape
+    if N < g.num_groups:
+        raise RuntimeError("sample_farthest_points: number of points must be >= num_samples")
+    fps_idx, centers = ops.fps(xyz32, g.num_groups)
+    knn_idx, _ = ops.knn(centers, xyz32, g.group_size)
+    src_feats = feats
+    if g.centralize_features:
+        raise NotImplementedError("centralize_features=True is not used by the released configs")
+    groups = ops.group_gather(xyz32, src_feats, centers, knn_idx, g.radius)
+    return dict(features=groups, centers=centers, knn_idx=knn_idx, fps_idx=fps_idx)
+
+
+# ------------------------------------------------------------------------------------------------
+# timm EVA / EVA02 blocks + PointCloudEncoder, pc_sam/model/pc_encoder.py:84-145
+# ------------------------------------------------------------------------------------------------
+class _PackedBlock:
+    def __init__(self, blk, D):
+        at = blk.attn
+        self.H, self.dh = at.num_heads, D // at.num_heads
+        self.g1, self.b1, self.eps1 = _f32(blk.norm1.weight), _f32(blk.norm1.bias), blk.norm1.eps
+        self.g2, self.b2, self.eps2 = _f32(blk.norm2.weight), _f32(blk.norm2.bias), blk.norm2.eps
+        dev = blk.norm1.weight.device
+        zeros = torch.zeros(D, dtype=torch.float32, device=dev)
+        if getattr(at, "qkv", None) is not None:
+            wqkv = at.qkv.weight.detach().float()
+            bqkv = torch.cat([at.q_bias.detach().float(), zeros, at.v_bias.detach().float()])
+        else:
+            wqkv = torch.cat([at.q_proj.weight, at.k_proj.weight, at.v_proj.weight]).detach().float()
+            bqkv = torch.cat([at.q_proj.bias.detach().float(), zeros, at.v_proj.bias.detach().float()])
+        self.wqkv, self.bqkv = ops.pack_weight(wqkv), bqkv.contiguous()
+        self.wproj, self.bproj = ops.pack_weight(at.proj.weight), _f32(at.proj.bias)
+        mlp = blk.mlp
+        self.swiglu = hasattr(mlp, "fc1_g")
+        if self.swiglu:
+            Hd = mlp.fc1_g.out_features
+            Hp = (Hd + 63) // 64 * 64
+            w1 = torch.zeros((2 * Hp, D), dtype=torch.float32, device=dev)
+            b1 = torch.zeros(2 * Hp, dtype=torch.float32, device=dev)
+            w1[:Hd], w1[Hp:Hp + Hd] = mlp.fc1_g.weight.detach().float(), mlp.fc1_x.weight.detach().float()
+            b1[:Hd], b1[Hp:Hp + Hd] = mlp.fc1_g.bias.detach().float(), mlp.fc1_x.bias.detach().float()
+            self.hid, self.hp = Hd, Hp
+            self.w1, self.bb1 = ops.pack_weight(w1), b1
+            self.gn, self.bn, self.epsn = _f32(mlp.norm.weight), _f32(mlp.norm.bias), mlp.norm.eps
+            w2 = torch.zeros((D, Hp), dtype=torch.float32, device=dev)
+            w2[:, :Hd] = mlp.fc2.weight.detach().float()
+            self.w2, self.bb2 = ops.pack_weight(w2), _f32(mlp.fc2.bias)
+        else:
+            self.hid = mlp.fc1.out_features
+            self.w1, self.bb1 = ops.pack_weight(mlp.fc1.weight), _f32(mlp.fc1.bias)
+            self.w2, self.bb2 = ops.pack_weight(mlp.fc2.weight), _f32(mlp.fc2.bias)
+
+
+class _PackedEncoder:
+    def __init__(self, enc):
+        D = enc.transformer_dim
+        self.D = D
+        self.wpp, self.bpp = ops.pack_weight(enc.patch_proj.weight), _f32(enc.patch_proj.bias)
+        self.wpos0, self.bpos0 = _f32(enc.pos_embed[0].weight), _f32(enc.pos_embed[0].bias)
+        self.wpos2, self.bpos2 = ops.pack_weight(enc.pos_embed[2].weight), _f32(enc.pos_embed[2].bias)
+        self.blocks = [_PackedBlock(b, D) for b in enc.transformer.blocks]
+        fn = enc.transformer.fc_norm
+        self.gf, self.bf, self.epsf = _f32(fn.weight), _f32(fn.bias), fn.eps
+        self.wout, self.bout = ops.pack_weight(enc.out_proj.weight), _f32(enc.out_proj.bias)
+
+
+def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
+    """x fp32 [B*L, D], updated in place (pre-LN residual block, rope=None)."""
+    dev = x.device
+    M = B * L
+    H, dh = pb.H, pb.dh
+    xn = Split(M, D, dev)
+    ops.layernorm(x, pb.g1, pb.b1, pb.eps1, out_split=xn)
+    qkv = Split(M, 3 * D, dev)
+    ops.gemm(xn, pb.wqkv, bias=pb.bqkv, out_split=qkv, passes=PASSES)
+    # V^T per (cloud, head): [B, H, dh, Lp]
+    Lp = (L + 63) // 64 * 64
+    vt = Split(B * H * dh, L, dev, pitch=Lp, zero=(Lp != L))
+    nv.check(nv.lib().psam_transpose_split(qkv.ptr(2 * D), qkv.plane, qkv.pitch, dh, L * qkv.pitch,
+                                           vt.ptr(), vt.plane, vt.pitch, dh * Lp, H * dh * Lp,
+                                           L, dh, H, B, nv.stream()), "transpose_split")
+    # S = Q K^T  (batched over heads and clouds), fp32 [B, H, L, L]
+    s = torch.empty((B * H * L, L), dtype=torch.float32, device=dev)
+    qa = qkv.operand(rows=L, k=dh, col=0, nb1=H, b1_stride=dh, nb2=B, b2_stride=L * qkv.pitch)
+    ka = qkv.operand(rows=L, k=dh, col=D, nb1=H, b1_stride=dh, nb2=B, b2_stride=L * qkv.pitch)
+    o = ops.GemmOut()
+    o.out_f32, o.ldo, o.out_b1, o.out_b2 = nv.ptr(s), L, L * L, H * L * L
+    o.alpha = 1.0
+    ops.gemm_raw(qa, ka, o, PASSES, 1)
+    p = Split(B * H * L, L, dev, pitch=Lp, zero=(Lp != L))
+    ops.softmax_split(s, L, dh ** -0.5, p)
+    # O = P V  -> heads recombined into [M, D]
+    att = Split(M, D, dev)
+    pa = p.operand(rows=L, k=L, nb1=H, b1_stride=L * Lp, nb2=B, b2_stride=H * L * Lp)
+    va = vt.operand(rows=dh, k=L, nb1=H, b1_stride=dh * Lp, nb2=B, b2_stride=H * dh * Lp)
+    o2 = ops.GemmOut()
+    o2.out_hi, o2.out_plane, o2.ldo_s, o2.outs_b1, o2.outs_b2 = att.ptr(), att.plane, att.pitch, dh, L * att.pitch
+    o2.alpha = 1.0
+    ops.gemm_raw(pa, va, o2, PASSES, 1)
+    # x += proj(att)
+    sk = _split_k_for(M, D, D)
+    if sk > 1:
+        ops.gemm(att, pb.wproj, bias=pb.bproj, out_f32=x, accumulate=True, split_k=sk, passes=PASSES)
+    else:
+        ops.gemm(att, pb.wproj, bias=pb.bproj, out_f32=x, resid=x, passes=PASSES)
+    # MLP
+    ops.layernorm(x, pb.g2, pb.b2, pb.eps2, out_split=xn)
+    if pb.swiglu:
+        gx = torch.empty((M, 2 * pb.hp), dtype=torch.float32, device=dev)
+        ops.gemm(xn, pb.w1, bias=pb.bb1, out_f32=gx, passes=PASSES)
+        h = Split(M, pb.hid, dev, pitch=pb.hp)
+        ops.swiglu_ln(gx, pb.hid, pb.hp, pb.gn, pb.bn, pb.epsn, h)
+    else:
+        h = Split(M, pb.hid, dev)
+        ops.gemm(xn, pb.w1, bias=pb.bb1, out_split=h, act=ACT_GELU, passes=PASSES)
+    sk = _split_k_for(M, D, pb.hid)
+    if sk > 1:
+        ops.gemm(h, pb.w2, bias=pb.bb2, out_f32=x, accumulate=True, split_k=sk, passes=PASSES)
+    else:
+        ops.gemm(h, pb.w2, bias=pb.bb2, out_f32=x, resid=x, passes=PASSES)
+
+
+def run_pc_encoder(enc, coords, features):
+    pk = _cached(enc, _PackedEncoder)
+    patches = run_knn_grouper(enc.patch_embed.grouper, coords, features)
+    emb, embs = run_patch_encoder(enc.patch_embed.patch_encoder, patches["features"], want_split=True)
+    patches["embeddings"] = emb
+    B, L, _ = emb.shape
+    D, dev = pk.D, emb.device
+    M = B * L
+    x = torch.empty((M, D), dtype=torch.float32, device=dev)
+    ops.gemm(embs, pk.wpp, bias=pk.bpp, out_f32=x, passes=PASSES)
+    pos = Split(M, pk.wpos0.shape[0], dev)
+    ops.small_in_linear(patches["centers"], pk.wpos0, pk.bpos0, None, None, 0.0, False, ACT_GELU, pos)
+    ops.gemm(pos, pk.wpos2, bias=pk.bpos2, out_f32=x, resid=x, passes=PASSES)
+    for pb in pk.blocks:
+        _run_block(pb, x, B, L, D)
+    xn = Split(M, D, dev)
+    ops.layernorm(x, pk.gf, pk.bf, pk.epsf, out_split=xn)
+    out = torch.empty((B, L, enc.embed_dim), dtype=torch.float32, device=dev)
+    ops.gemm(xn, pk.wout, bias=pk.bout, out_f32=out.view(M, -1), passes=PASSES)
+    return out, patches
+
+
+# ------------------------------------------------------------------------------------------------
+# prompt encoders, pc_sam/model/prompt_encoder.py:13-133
+# ------------------------------------------------------------------------------------------------
+_bad_flags = {}
+
+
+def bad_flag(device) -> torch.Tensor:
+    f = _bad_flags.get(device)
+    if f is None:
+        f = torch.zeros(1, dtype=torch.int32, device=device)
+        _bad_flags[device] = f
+    return f
+
+
+def raise_if_out_of_range(device):
+    """The reference raises inside PositionEmbeddingRandom.forward (host sync, prompt_encoder.py:44-46)."""
+    if torch.cuda.is_current_stream_capturing():
+        return
+    f = bad_flag(device)
+    if int(f.item()) != 0:
+        f.zero_()
+        raise ValueError("Input coordinates must be normalized to [-1, 1].")
+
+
+def run_pos_embedding(pe_layer, coords, labels=None, emb0=None, emb1=None, check=True):
+    c = coords.float().contiguous()
+    lab = labels.to(torch.int32).contiguous() if labels is not None else None
+    out = ops.posenc(c, _f32(pe_layer.positional_encoding_gaussian_matrix), lab, emb0, emb1, bad_flag(c.device))
+    if check:
+        raise_if_out_of_range(c.device)
+    return out
+
+
+def run_point_encoder(pe, points, labels, check=True):
+    assert points.shape[:-1] == labels.shape
+    return run_pos_embedding(pe.pe_layer, points, labels, _f32(pe.point_embeddings[0].weight),
+                             _f32(pe.point_embeddings[1].weight), check=check)
+
+
+def run_mask_encoder(me, masks, coords, centers, knn_idx, center_idx=None):
+    if masks is None:
+        return me.no_mask_embed.weight.reshape(1, 1, -1).expand(centers.shape[0], centers.shape[1], -1)
+    if me.centralize_features:
+        raise NotImplementedError("centralize_features=True is not used by the released configs")
+    m = masks.detach().float().contiguous().unsqueeze(-1)
+    groups = ops.group_gather(coords.float().contiguous(), m, centers, knn_idx, me.radius)
+    return run_patch_encoder(me.patch_encoder, groups)
+
+
+# ------------------------------------------------------------------------------------------------
+# two-way transformer + mask decoder, pc_sam/model/transformer.py, mask_decoder.py
+# ------------------------------------------------------------------------------------------------
+class _PackedAttn:
+    def __init__(self, a):
+        self.H = a.num_heads
+        self.inner = a.internal_dim
+        self.wq, self.bq = _f32(a.q_proj.weight), _f32(a.q_proj.bias)
+        self.wk, self.bk = _f32(a.k_proj.weight), _f32(a.k_proj.bias)
+        self.wv, self.bv = _f32(a.v_proj.weight), _f32(a.v_proj.bias)
+        self.wo, self.bo = _f32(a.out_proj.weight), _f32(a.out_proj.bias)
+
+
+def _ln(n):
+    return _f32(n.weight), _f32(n.bias), n.eps
+
+
+class _PackedDecoder:
+    def __init__(self, md):
+        tr = md.transformer
+        self.D = md.transformer_dim
+        self.layers = []
+        for l in tr.layers:
+            act = l.mlp.act
+            if isinstance(act, torch.nn.ReLU):
+                a = ACT_RELU
+            elif isinstance(act, torch.nn.GELU):
+                a = ACT_GELU
+            else:
+                raise NotImplementedError(f"MLPBlock activation {type(act)}")
+            self.layers.append(dict(
+                sa=_PackedAttn(l.self_attn), n1=_ln(l.norm1), t2i=_PackedAttn(l.cross_attn_token_to_image), n2=_ln(l.norm2),
+                w1=_f32(l.mlp.lin1.weight), b1=_f32(l.mlp.lin1.bias), w2=_f32(l.mlp.lin2.weight), b2=_f32(l.mlp.lin2.bias),
+                act=a, n3=_ln(l.norm3), n4=_ln(l.norm4), i2t=_PackedAttn(l.cross_attn_image_to_token), skip=l.skip_first_layer_pe))
+        self.final = _PackedAttn(tr.final_attn_token_to_image)
+        self.nf = _ln(tr.norm_final_attn)
+        self.iou_token, self.mask_tokens = _f32(md.iou_token.weight), _f32(md.mask_tokens.weight)
+        self.nmt = md.num_mask_tokens
+        self.hyper = []
+        for li in range(3):
+            self.hyper.append((torch.stack([_f32(m.layers[li].weight) for m in md.output_hypernetworks_mlps]).contiguous(),
+                               torch.stack([_f32(m.layers[li].bias) for m in md.output_hypernetworks_mlps]).contiguous()))
+        up = md.output_upscaling
+        self.up0w, self.up0b = _f32(up[0].weight), _f32(up[0].bias)
+        self.up1 = _ln(up[1])
+        self.up3w, self.up3b = ops.pack_weight(up[3].weight), _f32(up[3].bias)
+        self.iou = [(_f32(l.weight), _f32(l.bias)) for l in md.iou_prediction_head.layers]
+        self.iou_sigmoid = md.iou_prediction_head.sigmoid_output
+
+
+def _attend(pa: _PackedAttn, q_in, q_pe, k_in, k_pe, v_in, Z, Lq, Lk):
+    """Attention.forward (transformer.py:214-236); *_pe are optional addends fused into the projections."""
+    q = ops.linear_f32(q_in, pa.wq, pa.bq, x2=q_pe)
+    k = ops.linear_f32(k_in, pa.wk, pa.bk, x2=k_pe)
+    v = ops.linear_f32(v_in, pa.wv, pa.bv)
+    o = ops.attention_f32(q, k, v, Z, Lq, Lk, pa.H, pa.inner // pa.H)
+    return ops.linear_f32(o, pa.wo, pa.bo)
+
+
+def _add_ln(x, r, n):
+    out = torch.empty_like(x)
+    ops.layernorm(x, n[0], n[1], n[2], r=r, out_f32=out)
+    return out
+
+
+def run_mask_decoder(md, pc_embeddings, pc_pe, sparse, dense, aux, multimask_output: bool):
+    pk = _cached(md, _PackedDecoder)
+    dev = pc_embeddings.device
+    D = pk.D
+    Z, P, _ = sparse.shape
+    B, G, _ = pc_embeddings.shape
+    rep = Z // B
+    T = 1 + pk.nmt + P
+    mask_slice = slice(1, None) if multimask_output else slice(0, 1)
+    ids = list(range(pk.nmt))[mask_slice]
+    C = len(ids)
+
+    # tokens / src (mask_decoder.py:126-139)
+    sparse = sparse.float().contiguous()
+    pc_embeddings = pc_embeddings.float().contiguous()
+    if dense.stride(0) == 0 and dense.stride(1) == 0:  # no-mask embedding broadcast
+        dense_t, dz, dg = dense[0, 0].contiguous(), 0, 0
+    else:
+        dense_t = dense.float().contiguous()
+        dz, dg = (G * D if dense_t.shape[0] == Z else 0), D
+        if dense_t.shape[0] not in (Z, 1):
+            raise RuntimeError("dense prompt embeddings must have batch B*M (or 1)")
+    tokens = torch.empty((Z * T, D), dtype=torch.float32, device=dev)
+    src = torch.empty((Z * G, D), dtype=torch.float32, device=dev)
+    nv.check(nv.lib().psam_decoder_prepare(nv.ptr(pk.iou_token), nv.ptr(pk.mask_tokens), pk.nmt, nv.ptr(sparse), P,
+                                           nv.ptr(pc_embeddings), nv.ptr(dense_t), dz, dg, Z, rep, G, D,
+                                           nv.ptr(tokens), nv.ptr(src), nv.stream()), "decoder_prepare")
+    pe_z = ops.add_bcast(torch.zeros_like(src), pc_pe.float().contiguous(), chunk=G * D, rep=rep)  # repeat_interleave(pc_pe)
+
+    queries, keys, qpe = tokens, src, tokens
+    for l in pk.layers:
+        if l["skip"]:
+            queries = _add_ln(_attend(l["sa"], queries, None, queries, None, queries, Z, T, T), None, l["n1"])
+        else:
+            queries = _add_ln(queries, _attend(l["sa"], queries, qpe, queries, qpe, queries, Z, T, T), l["n1"])
+        queries = _add_ln(queries, _attend(l["t2i"], queries, qpe, keys, pe_z, keys, Z, T, G), l["n2"])
+        h = ops.linear_f32(queries, l["w1"], l["b1"], act=l["act"])
+        queries = _add_ln(queries, ops.linear_f32(h, l["w2"], l["b2"]), l["n3"])
+        keys = _add_ln(keys, _attend(l["i2t"], keys, pe_z, queries, qpe, queries, Z, G, T), l["n4"])
+    queries = _add_ln(queries, _attend(pk.final, queries, qpe, keys, pe_z, keys, Z, T, G), pk.nf)
+    hs = queries  # [Z*T, D]
+
+    # upscaling (mask_decoder.py:146-164): Linear0 commutes with the (affine, weights sum to 1) interpolation
+    if aux.interp_index is None or aux.interp_weight is None:
+        aux.interp_index, aux.interp_weight = ops.knn3_interp(aux.coords.float().contiguous(), aux.centers)
+    N = aux.coords.shape[1]
+    f0 = ops.linear_f32(keys, pk.up0w, pk.up0b)  # [Z*G, D]
+    u1 = Split(Z * N, D, dev)
+    nv.check(nv.lib().psam_interp_ln_gelu(nv.ptr(f0), Z, rep, G, D, nv.ptr(aux.interp_index), nv.ptr(aux.interp_weight), N,
+                                          nv.ptr(pk.up1[0]), nv.ptr(pk.up1[1]), pk.up1[2], u1.ptr(), u1.plane, u1.pitch,
+                                          nv.stream()), "interp_ln_gelu")
+    u2 = torch.empty((Z * N, D), dtype=torch.float32, device=dev)
+    ops.gemm(u1, pk.up3w, bias=pk.up3b, out_f32=u2, act=ACT_GELU, passes=PASSES)
+
+    # hyper-network MLPs on the selected mask tokens (mask_decoder.py:167-175), batched over tokens
+    i0 = ids[0]
+    x = hs
+    ld = T * D
+    xoff = (1 + i0) * D
+    hyper = None
+    for li, (w, b) in enumerate(pk.hyper):
+        y = torch.empty((Z, C, D), dtype=torch.float32, device=dev)
+        ops.linear_f32(x, w[i0:i0 + C], b[i0:i0 + C], act=ACT_RELU if li < 2 else ACT_NONE, out=y, M=Z, K=D, ldx=ld, Z=C,
+                       x_z=D, w_z=D * D, b_z=D, y_z=D, ldy=C * D, x_off=xoff)
+        x, ld, xoff, hyper = y, C * D, 0, y
+    masks = torch.empty((Z, C, N), dtype=torch.float32, device=dev)
+    nv.check(nv.lib().psam_mask_dot(nv.ptr(u2), D, nv.ptr(hyper), Z, C, N, D, nv.ptr(masks), nv.stream()), "mask_dot")
+
+    # IoU head on the iou token (mask_decoder.py:180-182)
+    y = hs
+    ld = T * D
+    for li, (w, b) in enumerate(pk.iou):
+        y = ops.linear_f32(y, w, b, act=ACT_RELU if li < len(pk.iou) - 1 else ACT_NONE, M=Z, K=w.shape[1], ldx=ld)
+        ld = y.shape[-1]
+    if pk.iou_sigmoid:
+        y = torch.sigmoid(y)
+    return masks, y[:, mask_slice].contiguous()

@@ -1,0 +1,333 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against the oracle / plain torch fp32."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import synth, tokenizer_ref, torch_ref  # noqa: E402
+
+
+def _ops():
+    from psam_b200 import ops
+
+    return ops
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------------------------------------
+# FPS
+# ------------------------------------------------------------------------------------------------
+def test_fps_golden_fixtures(golden_dir):
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, "fps_cases.npz"))
+    for i in range(int(g["n"])):
+        B, N, G, seed = [int(v) for v in g[f"case{i}"]]
+        xyz, _ = synth.make_batch(B, N, seed, str(g[f"kind{i}"]))
+        idx, centers = ops.fps(xyz.to(_dev()), G)
+        want = torch.from_numpy(g[f"idx{i}"].astype(np.int64))
+        got = idx.cpu()
+        nbad = int((got != want).sum())
+        assert nbad == 0, f"case {i} {(B, N, G)}: {nbad} mismatches, first at {(got != want).nonzero()[:3].tolist()}"
+        ref_c = torch.gather(xyz, 1, want[..., None].expand(-1, -1, 3))
+        assert torch.equal(centers.cpu(), ref_c)
+
+
+@pytest.mark.parametrize("B,N,G,kind", [(1, 32768, 512, "ball"), (3, 5000, 256, "grid"), (2, 70000, 64, "ball"),
+                                        (1, 131072, 96, "kitti"), (2, 100, 100, "ball"), (1, 33, 7, "grid")])
+def test_fps_vs_oracle(B, N, G, kind):
+    ops = _ops()
+    xyz, _ = synth.make_batch(B, N, 7, kind)
+    idx, _ = ops.fps(xyz.to(_dev()), G)
+    want = tokenizer_ref.fps(xyz.numpy(), G)
+    assert (idx.cpu().numpy() == want).all()
+
+
+def test_fps_degenerate_and_errors():
+    ops = _ops()
+    same = torch.ones(1, 40, 3, device=_dev())
+    idx, _ = ops.fps(same, 5)
+    assert (idx == 0).all()
+    with pytest.raises(RuntimeError):
+        ops.fps(torch.zeros(1, 4, 3, device=_dev()), 5)
+    from pc_sam.model.common import sample_farthest_points
+
+    with pytest.raises(RuntimeError):
+        sample_farthest_points(torch.zeros(1, 4, 3), 2)  # CPU tensor: no fallback
+
+
+def test_fps_against_reference_cuda_kernel():
+    """The reference's own kernel compiled for sm_100a (oracle/_ref, built by oracle/build_ref.py)."""
+    from oracle import build_ref
+
+    ref = build_ref.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    ops = _ops()
+    for (B, N, G, kind, seed) in [(2, 4096, 128, "grid", 1), (1, 700, 64, "grid", 2), (4, 1024, 512, "ball", 3),
+                                  (1, 32768, 512, "ball", 4), (2, 3000, 300, "grid", 5), (1, 50, 50, "grid", 6)]:
+        xyz, _ = synth.make_batch(B, N, seed, kind)
+        x = xyz.to(_dev())
+        want = ref.sample_farthest_points_cuda(x, G).cpu()
+        got, _ = ops.fps(x, G)
+        assert torch.equal(got.cpu(), want), (B, N, G, kind)
+        assert (tokenizer_ref.fps(xyz.numpy(), G) == want.numpy()).all(), "oracle vs reference kernel"
+
+
+# ------------------------------------------------------------------------------------------------
+# kNN / grouping / interpolation
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,Q,K,kind", [(2, 4096, 128, 32, "ball"), (1, 32768, 512, 64, "ball"), (1, 777, 24, 8, "ball"),
+                                          (1, 2048, 64, 32, "grid"), (1, 20000, 64, 256, "kitti"), (2, 300, 40, 3, "ball"),
+                                          (1, 64, 64, 64, "ball"), (1, 5000, 16, 1, "ball")])
+def test_knn_vs_oracle(B, N, Q, K, kind):
+    ops = _ops()
+    xyz, _ = synth.make_batch(B, N, 11, kind)
+    centers = xyz[:, torch.randperm(N, generator=torch.Generator().manual_seed(0))[:Q]].contiguous()
+    idx, d2 = ops.knn(centers.to(_dev()), xyz.to(_dev()), K, want_d2=True)
+    widx, wd2 = tokenizer_ref.knn(centers.numpy(), xyz.numpy(), K)
+    # distances are a multiset property (independent of tie resolution): must agree bit for bit
+    assert np.array_equal(d2.cpu().numpy(), wd2), f"max diff {np.abs(d2.cpu().numpy() - wd2).max()}"
+    # both sides resolve ties towards the lower index and sort by (d2, index): indices agree exactly
+    assert np.array_equal(idx.cpu().numpy(), widx)
+    # and the reference semantics (cdist + topk) select the same sets where no tie exists
+    if kind != "grid":
+        _, ref = torch_ref.knn_points(centers, xyz, K, sorted=True)
+        assert np.array_equal(np.sort(ref.numpy(), -1), np.sort(widx, -1))
+
+
+def test_group_gather_and_interp():
+    ops = _ops()
+    xyz, feats = synth.make_batch(2, 3000, 3)
+    g = torch_ref.KNNGrouper(64, 16)
+    want = g(xyz, feats)
+    d = _dev()
+    idx, centers = ops.fps(xyz.to(d), 64)
+    knn, _ = ops.knn(centers, xyz.to(d), 16)
+    groups = ops.group_gather(xyz.to(d), feats.to(d), centers, knn)
+    # same neighbour sets -> compare after sorting rows of each group by neighbour index
+    o1 = torch.argsort(knn.cpu(), -1)
+    o2 = torch.argsort(want["knn_idx"], -1)
+    a = torch.gather(groups.cpu(), 2, o1[..., None].expand(-1, -1, -1, 6))
+    b = torch.gather(want["features"], 2, o2[..., None].expand(-1, -1, -1, 6))
+    assert torch.equal(torch.sort(knn.cpu(), -1).values, torch.sort(want["knn_idx"], -1).values)
+    torch.testing.assert_close(a, b, atol=0, rtol=0)
+    # mask-encoder form: M=2 masks per cloud, 1 channel, radius
+    m = torch.randn(4, 3000, 1)
+    want2 = torch_ref.group_with_centers_and_knn(xyz, m, want["centers"], knn.cpu(), radius=0.5)
+    got2 = ops.group_gather(xyz.to(d), m.to(d), centers, knn, 0.5)
+    torch.testing.assert_close(got2.cpu(), want2, atol=1e-7, rtol=1e-6)
+    # 3-NN interpolation weights
+    ii, ww = ops.knn3_interp(xyz.to(d), centers)
+    wi, wwt = torch_ref.compute_interp_weights(xyz, want["centers"])
+    assert torch.equal(torch.sort(ii.cpu(), -1).values, torch.sort(wi, -1).values)
+    torch.testing.assert_close(torch.sort(ww.cpu(), -1).values, torch.sort(wwt, -1).values, atol=2e-6, rtol=1e-5)
+
+
+def test_nn_distance_vs_reference_and_bruteforce():
+    ops = _ops()
+    xyz, _ = synth.make_batch(1, 5000, 9)
+    a, b = xyz[0, :1800].to(_dev()), xyz[0, 1800:].to(_dev())
+    got = ops.nn_distance(a, b)
+    want = (torch.cdist(a.cpu().double(), b.cpu().double()) ** 2).min(dim=1).values.float()
+    torch.testing.assert_close(got.cpu(), want, atol=1e-7, rtol=1e-5)
+    from oracle import build_ref
+
+    ref = build_ref.load_ref()
+    if ref is not None:
+        d1 = ref.chamfer_distance_forward_cuda(a[None], b[None])[0][0]
+        torch.testing.assert_close(got, d1, atol=1e-7, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 GEMM
+# ------------------------------------------------------------------------------------------------
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(_dev())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (512, 1024, 1024), (300, 200, 2730), (4096, 128, 128),
+                                   (256, 64, 64), (77, 344, 128), (512, 5504, 1024), (1, 256, 512)])
+def test_gemm_tc_plain(M, N, K):
+    ops = _ops()
+    a, w, b = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5), _rand(N, seed=3)
+    A, W = ops.pack_weight(a), ops.pack_weight(w)
+    # the packed operands reproduce fp32 to 2^-17
+    assert float((A.float() - a).abs().max() / a.abs().max()) < 2 ** -16
+    out = torch.empty(M, N, device=_dev())
+    ops.gemm(A, W, bias=b, out_f32=out)
+    want = (a.double() @ w.double().t() + b.double()).float()
+    err = float((out - want).abs().max())
+    scale = float(want.abs().max())
+    assert err < 3e-5 * max(scale, 1.0), f"err {err} scale {scale}"
+    # single-pass bf16 mode exists and is (much) less accurate
+    out1 = torch.empty(M, N, device=_dev())
+    ops.gemm(A, W, bias=b, out_f32=out1, passes=1)
+    err1 = float((out1 - want).abs().max())
+    assert err1 < 3e-2 * max(scale, 1.0)
+
+
+def test_gemm_tc_epilogues_and_splitk():
+    ops = _ops()
+    M, N, K = 512, 1024, 2730
+    a, w, b = _rand(M, K, seed=4), _rand(N, K, seed=5, scale=K ** -0.5), _rand(N, seed=6)
+    A, W = ops.pack_weight(a), ops.pack_weight(w)
+    base = (a.double() @ w.double().t() + b.double())
+    r = _rand(M, N, seed=7)
+    # residual in place
+    x = r.clone()
+    ops.gemm(A, W, bias=b, out_f32=x, resid=x)
+    assert float((x - (base + r.double()).float()).abs().max()) < 1e-4
+    # split-K accumulate (red.add) into the residual stream
+    for sk in (2, 4, 7):
+        x = r.clone()
+        ops.gemm(A, W, bias=b, out_f32=x, accumulate=True, split_k=sk)
+        assert float((x - (base + r.double()).float()).abs().max()) < 1e-4, sk
+    # GELU + split output + fp32 output together
+    o32 = torch.empty(M, N, device=_dev())
+    osp = ops.Split(M, N, _dev())
+    ops.gemm(A, W, bias=b, out_f32=o32, out_split=osp, act=ops.ACT_GELU)
+    want = torch.nn.functional.gelu(base.float())
+    assert float((o32 - want).abs().max()) < 1e-4
+    assert float((osp.float() - o32).abs().max()) < 2e-5 * float(want.abs().max())
+    # alpha
+    o = torch.empty(M, N, device=_dev())
+    ops.gemm(A, W, out_f32=o, alpha=0.125)
+    assert float((o - (0.125 * (base - b.double())).float()).abs().max()) < 1e-4
+
+
+def test_gemm_tc_batched_attention_shapes():
+    """The batched operand views used by the ViT attention (heads = b1, clouds = b2)."""
+    from psam_b200 import native as nv
+
+    ops = _ops()
+    B, H, L, dh = 2, 3, 200, 88
+    D = H * dh
+    qkv = _rand(B * L, 3 * D, seed=8)
+    QKV = ops.Split(B * L, 3 * D, _dev())
+    ops.split_f32(qkv, QKV)
+    s = torch.empty(B * H * L, L, device=_dev())
+    qa = QKV.operand(rows=L, k=dh, col=0, nb1=H, b1_stride=dh, nb2=B, b2_stride=L * QKV.pitch)
+    ka = QKV.operand(rows=L, k=dh, col=D, nb1=H, b1_stride=dh, nb2=B, b2_stride=L * QKV.pitch)
+    o = ops.GemmOut()
+    o.out_f32, o.ldo, o.out_b1, o.out_b2, o.alpha = nv.ptr(s), L, L * L, H * L * L, 1.0
+    ops.gemm_raw(qa, ka, o, 3, 1)
+    q = qkv[:, :D].reshape(B, L, H, dh).permute(0, 2, 1, 3).double()
+    k = qkv[:, D:2 * D].reshape(B, L, H, dh).permute(0, 2, 1, 3).double()
+    want = (q @ k.transpose(-1, -2)).float().reshape(B * H * L, L)
+    assert float((s - want).abs().max()) < 3e-4, float((s - want).abs().max())
+
+
+# ------------------------------------------------------------------------------------------------
+# glue kernels
+# ------------------------------------------------------------------------------------------------
+def test_layernorm_variants():
+    ops = _ops()
+    x, r = _rand(1000, 2730, seed=1), _rand(1000, 2730, seed=2)
+    g, b = _rand(2730, seed=3), _rand(2730, seed=4)
+    out = torch.empty_like(x)
+    sp = ops.Split(1000, 2730, _dev(), pitch=2752)
+    ops.layernorm(x, g, b, 1e-6, r=r, out_f32=out, out_split=sp)
+    want = torch.nn.functional.layer_norm(x + r, (2730,), g, b, 1e-6)
+    torch.testing.assert_close(out, want, atol=2e-5, rtol=1e-5)
+    assert float((sp.float() - want).abs().max()) < 1e-4
+    assert float(sp.t[:, :, 2730:].float().abs().max()) == 0.0
+    # group bias + GELU (PatchEncoder conv2[1..2])
+    t = _rand(10, 2730, seed=5)
+    ops.layernorm(x, g, b, 1e-5, gbias=t, group_rows=100, act=ops.ACT_GELU, out_f32=out)
+    want = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x + t.repeat_interleave(100, 0), (2730,), g, b, 1e-5))
+    torch.testing.assert_close(out, want, atol=2e-5, rtol=1e-5)
+
+
+def test_swiglu_small_in_groupmax_softmax_transpose():
+    ops = _ops()
+    d = _dev()
+    H, Hp, M = 344, 384, 77
+    gx = _rand(M, 2 * Hp, seed=1)
+    g, b = _rand(H, seed=2), _rand(H, seed=3)
+    out = ops.Split(M, H, d, pitch=Hp)
+    ops.swiglu_ln(gx, H, Hp, g, b, 1e-6, out)
+    want = torch.nn.functional.layer_norm(torch.nn.functional.silu(gx[:, :H]) * gx[:, Hp:Hp + H], (H,), g, b, 1e-6)
+    assert float((out.float() - want).abs().max()) < 5e-5
+    assert float(out.t[:, :, H:].float().abs().max()) == 0.0
+    # small-input linear (+LN+GELU)
+    x = _rand(500, 6, seed=4)
+    W, bb, gg, be = _rand(128, 6, seed=5), _rand(128, seed=6), _rand(128, seed=7), _rand(128, seed=8)
+    o = ops.Split(500, 128, d)
+    ops.small_in_linear(x, W, bb, gg, be, 1e-5, True, ops.ACT_GELU, o)
+    want = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x @ W.t() + bb, (128,), gg, be, 1e-5))
+    assert float((o.float() - want).abs().max()) < 5e-5
+    o = ops.Split(500, 128, d)
+    ops.small_in_linear(x[:, :3].contiguous(), W[:, :3].contiguous(), bb, None, None, 0.0, False, ops.ACT_GELU, o)
+    want = torch.nn.functional.gelu(x[:, :3] @ W[:, :3].t() + bb)
+    assert float((o.float() - want).abs().max()) < 5e-5
+    # group max
+    x = _rand(30 * 16, 200, seed=9)
+    y = torch.empty(30, 200, device=d)
+    ys = ops.Split(30, 200, d)
+    ops.group_max(x, 30, 16, out_f32=y, out_split=ys)
+    want = x.reshape(30, 16, 200).max(1).values
+    assert torch.equal(y, want)
+    assert float((ys.float() - want).abs().max()) < 1e-4
+    # softmax
+    s = _rand(300, 200, seed=10, scale=3.0)
+    p = ops.Split(300, 200, d, pitch=256, zero=True)
+    ops.softmax_split(s, 200, 0.125, p)
+    assert float((p.float() - torch.softmax(s * 0.125, -1)).abs().max()) < 2e-6
+    # transpose of split planes per (head, cloud)
+    B, Hh, L, dh = 2, 3, 50, 16
+    src = ops.Split(B * L, 3 * Hh * dh, d)
+    ops.split_f32(_rand(B * L, 3 * Hh * dh, seed=11), src)
+    Lp = 64
+    dst = ops.Split(B * Hh * dh, L, d, pitch=Lp, zero=True)
+    from psam_b200 import native as nv
+
+    nv.check(nv.lib().psam_transpose_split(src.ptr(2 * Hh * dh), src.plane, src.pitch, dh, L * src.pitch, dst.ptr(), dst.plane,
+                                           dst.pitch, dh * Lp, Hh * dh * Lp, L, dh, Hh, B, nv.stream()), "transpose")
+    v = src.float()[:, 2 * Hh * dh:].reshape(B, L, Hh, dh).permute(0, 2, 3, 1).reshape(B * Hh * dh, L)
+    assert torch.equal(dst.float(), v)
+
+
+def test_linear_attention_posenc_misc():
+    ops = _ops()
+    d = _dev()
+    x, x2, w, b, r = _rand(70, 256, seed=1), _rand(70, 256, seed=2), _rand(130, 256, seed=3, scale=0.06), _rand(130, seed=4), _rand(70, 130, seed=5)
+    y = ops.linear_f32(x, w, b, x2=x2, r=r, act=ops.ACT_RELU)
+    want = torch.relu((x + x2) @ w.t() + b) + r
+    torch.testing.assert_close(y, want, atol=2e-5, rtol=1e-5)
+    # attention
+    Z, Lq, Lk, H, dh = 3, 7, 100, 8, 16
+    q, k, v = _rand(Z * Lq, H * dh, seed=6), _rand(Z * Lk, H * dh, seed=7), _rand(Z * Lk, H * dh, seed=8)
+    o = ops.attention_f32(q, k, v, Z, Lq, Lk, H, dh)
+    qq = q.reshape(Z, Lq, H, dh).transpose(1, 2)
+    kk = k.reshape(Z, Lk, H, dh).transpose(1, 2)
+    vv = v.reshape(Z, Lk, H, dh).transpose(1, 2)
+    want = (torch.softmax(qq @ kk.transpose(-1, -2) / math.sqrt(dh), -1) @ vv).transpose(1, 2).reshape(Z * Lq, H * dh)
+    torch.testing.assert_close(o, want, atol=2e-5, rtol=1e-4)
+    # positional encoding + labels + range flag
+    pe = torch_ref.PointEncoder(256)
+    c = (torch.rand(4, 5, 3) * 2 - 1)
+    lab = torch.tensor([[1, 0, 1, 0, 1]] * 4)
+    want = pe(c, lab)
+    from psam_b200 import engine
+
+    got = ops.posenc(c.to(d), pe.pe_layer.positional_encoding_gaussian_matrix.to(d), lab.to(d).int(),
+                     pe.point_embeddings[0].weight.detach().to(d), pe.point_embeddings[1].weight.detach().to(d),
+                     engine.bad_flag(d))
+    torch.testing.assert_close(got.cpu(), want.detach(), atol=3e-5, rtol=1e-5)
+    engine.raise_if_out_of_range(d)
+    ops.posenc((c * 3).to(d), pe.pe_layer.positional_encoding_gaussian_matrix.to(d), None, None, None, engine.bad_flag(d))
+    with pytest.raises(ValueError):
+        engine.raise_if_out_of_range(d)
+    # broadcast add
+    a, bb = _rand(4 * 6 * 8, seed=9), _rand(2 * 6 * 8, seed=10)
+    got = ops.add_bcast(a, bb, chunk=6 * 8, rep=2)
+    want = a.reshape(4, 48) + bb.reshape(2, 48).repeat_interleave(2, 0)
+    torch.testing.assert_close(got.reshape(4, 48), want, atol=0, rtol=0)
