@@ -19,7 +19,7 @@ def make_cloud(n: int, seed: int = 0, cloud_id: int = 0, kind: str = "ball"):
         xyz[:k, 2] = xyz[:, 2].min()
     elif kind == "grid":  # tie-heavy: quantised to a 1/64 grid with duplicated points
         xyz = torch.round(xyz * 16) / 16
-        xyz[n // 2:] = xyz[: n - n // 2]
+        xyz[n // 2:] = xyz[: n - n // 2].clone()
     xyz = xyz - xyz.mean(dim=0, keepdim=True)
     xyz = xyz / xyz.norm(dim=1).max()
     feats = torch.rand(n, 3, generator=g) * 2 - 1

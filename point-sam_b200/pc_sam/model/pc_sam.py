@@ -79,6 +79,13 @@ class PointCloudSAM(nn.Module):
         return self._decode(enc, a["prompt_coords"], a["prompt_labels"], a.get("prompt_masks"),
                             bool(a.get("multimask_output", True)))
 
+    def make_predictor(self, batch_size: int, num_points: int, num_prompts: int, multimask_output: bool = True,
+                       use_graph: bool = True):
+        """Fixed-shape predictor that replays the whole path as one CUDA graph (serving entry point)."""
+        from psam_b200.predictor import GraphPredictor
+
+        return GraphPredictor(self, batch_size, num_points, num_prompts, multimask_output, use_graph)
+
     # ------------------------------------------------------------------------------------------
     def predict_iterative(self, coords, features, prompt_coords_seq: List[torch.Tensor],
                           prompt_labels_seq: List[torch.Tensor]) -> List[Dict[str, torch.Tensor]]:

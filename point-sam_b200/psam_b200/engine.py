@@ -214,7 +214,7 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
     if pb.swiglu:
         gx = torch.empty((M, 2 * pb.hp), dtype=torch.float32, device=dev)
         ops.gemm(xn, pb.w1, bias=pb.bb1, out_f32=gx, passes=PASSES)
-        h = Split(M, pb.hid, dev, pitch=pb.hp)
+        h = Split(M, pb.hp, dev, pitch=pb.hp)  # columns hid..hp are zero-filled by swiglu_ln
         ops.swiglu_ln(gx, pb.hid, pb.hp, pb.gn, pb.bn, pb.epsn, h)
     else:
         h = Split(M, pb.hid, dev)

@@ -117,7 +117,11 @@ def ptr(t) -> int:
     return t.data_ptr()
 
 
+LAUNCHES = [0]  # kernels launched through the C ABI (each successful call is exactly one launch)
+
+
 def check(rc: int, what: str):
+    LAUNCHES[0] += 1
     if rc != 0:
         kind = "invalid argument" if rc == -1 else ("unsupported configuration" if rc == -2 else f"CUDA error {rc}")
         raise RuntimeError(f"psam_b200.{what} failed: {kind}")

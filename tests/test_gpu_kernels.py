@@ -255,7 +255,7 @@ def test_swiglu_small_in_groupmax_softmax_transpose():
     out = ops.Split(M, H, d, pitch=Hp)
     ops.swiglu_ln(gx, H, Hp, g, b, 1e-6, out)
     want = torch.nn.functional.layer_norm(torch.nn.functional.silu(gx[:, :H]) * gx[:, Hp:Hp + H], (H,), g, b, 1e-6)
-    assert float((out.float() - want).abs().max()) < 5e-5
+    assert float((out.float() - want).abs().max()) < 2e-5 * float(want.abs().max()) + 1e-6
     assert float(out.t[:, :, H:].float().abs().max()) == 0.0
     # small-input linear (+LN+GELU)
     x = _rand(500, 6, seed=4)
