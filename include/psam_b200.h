@@ -97,6 +97,15 @@ typedef struct {
 int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, const psam_gemm_out* out, int passes, int split_k,
                      cudaStream_t stream);
 
+/* Fused encoder self-attention on tensor cores: out = softmax(Q K^T * scale) V per (cloud, head); exact two-pass
+ * softmax with S resident in tensor memory.  q/k/v are split-bf16 operand views [L rows x dh] with nb1 = heads,
+ * nb2 = clouds (typically three column windows of the fused qkv activation).  Supports dh == 64 and L <= 512
+ * (returns PSAM_ERR_UNSUPPORTED otherwise - the caller then uses psam_gemm_bf16x3 + psam_softmax_split).
+ * Replaces F.scaled_dot_product_attention in timm EvaAttention (blocks called at pc_encoder.py:138-139). */
+int psam_attention_bf16x3(const psam_operand* q, const psam_operand* k, const psam_operand* v, void* out_hi,
+                          long long out_plane, long long ldo, long long out_head_stride, long long out_cloud_stride,
+                          float scale, cudaStream_t stream);
+
 /* Small fp32 SIMT linear for the prompt decoder (rows < one MMA tile):
  * Y[z][M,N] = act((X[z] (+X2[z]))[M,K] * W[z][N,K]^T + b[z]) (+R[z]); strides in elements; any pointer
  * stride may be 0 to broadcast.  Replaces nn.Linear in transformer.py:199-202,239-253 and the MLP

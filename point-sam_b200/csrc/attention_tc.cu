@@ -1,0 +1,300 @@
+// Fused multi-head self-attention for sm_100a (encoder blocks): O = softmax(Q K^T * scale) V.
+//
+// Replaces F.scaled_dot_product_attention inside timm's EvaAttention (called from
+// pc_sam/model/pc_encoder.py:138-139 via block(x); rope=None, no mask) and the four unfused kernels of
+// the first implementation (QK^T GEMM, softmax, V transpose, PV GEMM).
+//
+// One CTA per (cloud, head, 128-query tile).  All key blocks of the row fit the tensor memory
+// (L <= 512 keys -> S is 128 x 512 fp32 = the full 512 TMEM columns), so softmax is EXACT two-pass
+// (row max over all keys, then exp) - no online rescaling:
+//   warp 0    TMA producer: Q tile once, then K blocks, then V blocks through a 3-stage ring
+//             (each stage = one 128-row x 64 block, hi+lo planes, 32 KB)
+//   warp 1    MMA issuer: S_j = Q K_j^T (split-bf16, 3 passes) into TMEM columns [128j,128j+128);
+//             later O += P_j V_j with P from shared memory (K-major) and V^T taken directly from the
+//             row-major V block as an MN-major B operand (no transpose pass); O reuses columns [0,64)
+//   warps 2-5 softmax: thread = query row; tcgen05.ld S, row max, exp2, split P into bf16 hi/lo and
+//             write it 128B-swizzled into shared memory for the PV MMA; finally O / rowsum -> split-bf16
+// Numerics follow the split-bf16 scheme of gemm_tc.cu (x ~= hi + lo, three MMA passes).
+#include "psam_common.cuh"
+#include "../../include/psam_b200.h"
+
+namespace psam {
+
+constexpr int ATT_BQ = 128;        // queries per CTA
+constexpr int ATT_BKEY = 128;      // keys per block
+constexpr int ATT_DH = 64;         // head dim handled by this kernel
+constexpr int ATT_STAGES = 3;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TILE = 128 * 64 * 2;                 // one 128x64 bf16 tile (one plane)
+constexpr int ATT_SMEM_Q = 2 * ATT_TILE;               // hi + lo
+constexpr int ATT_SMEM_STAGE = 2 * ATT_TILE;           // hi + lo of a K or V block
+constexpr int ATT_SMEM_P = 2 * 2 * ATT_TILE;           // hi + lo, 2 k-blocks of 64 keys
+constexpr int ATT_SMEM_TOTAL = ATT_SMEM_Q + ATT_STAGES * ATT_SMEM_STAGE + ATT_SMEM_P + 1024;
+
+// MN-major (N contiguous), 128B-swizzled B operand: rows of the tile are K (keys), 64 N-elements = 128 B per
+// row, 8-row swizzle atoms 1024 B apart along K.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(16384 >> 4) << 16;  // leading byte offset: next 64-wide N atom (unused, N = 64)
+    d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset: next 8-row group along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+struct AttnParams {
+    int L, H, B;
+    float scale_log2e;  // softmax scale * log2(e)
+    __nv_bfloat16* out_hi;
+    long long out_plane, ldo, out_h, out_b;  // elements: plane offset, row stride, head / cloud strides
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t q_full, s_full, p_full, p_empty, o_full;
+    __shared__ __align__(8) uint64_t kv_full[ATT_STAGES], kv_empty[ATT_STAGES];
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t sQ = smem_base;
+    const uint32_t sKV = sQ + ATT_SMEM_Q;
+    const uint32_t sP = sKV + ATT_STAGES * ATT_SMEM_STAGE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int nkb = (p.L + ATT_BKEY - 1) / ATT_BKEY;  // key blocks (<= 4)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+        mbar_init(smem_u32(&q_full), 1);
+        mbar_init(smem_u32(&s_full), 1);
+        mbar_init(smem_u32(&p_full), 128);
+        mbar_init(smem_u32(&p_empty), 1);
+        mbar_init(smem_u32(&o_full), 1);
+        for (int s = 0; s < ATT_STAGES; ++s) {
+            mbar_init(smem_u32(&kv_full[s]), 1);
+            mbar_init(smem_u32(&kv_empty[s]), 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t qb = smem_u32(&q_full);
+            mbar_arrive_expect_tx(qb, ATT_SMEM_Q);
+            tma_load_5d(sQ, &tmap_q, qb, 0, q_tile * ATT_BQ, 0, h, b);
+            tma_load_5d(sQ + ATT_TILE, &tmap_q, qb, 0, q_tile * ATT_BQ, 1, h, b);
+            for (int i = 0; i < 2 * nkb; ++i) {  // K blocks then V blocks
+                const int s = i % ATT_STAGES;
+                const uint32_t ph = (uint32_t)(i / ATT_STAGES) & 1u;
+                mbar_wait(smem_u32(&kv_empty[s]), ph ^ 1u);
+                const uint32_t fb = smem_u32(&kv_full[s]);
+                mbar_arrive_expect_tx(fb, ATT_SMEM_STAGE);
+                const CUtensorMap* tm = (i < nkb) ? &tmap_k : &tmap_v;
+                const int j = (i < nkb) ? i : i - nkb;
+                tma_load_5d(sKV + s * ATT_SMEM_STAGE, tm, fb, 0, j * ATT_BKEY, 0, h, b);
+                tma_load_5d(sKV + s * ATT_SMEM_STAGE + ATT_TILE, tm, fb, 0, j * ATT_BKEY, 1, h, b);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, ATT_BKEY);                   // S: A,B K-major
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_DH) | (1u << 16);        // O: B (V) MN-major
+        mbar_wait(smem_u32(&q_full), 0);
+        tc_fence_after();
+        const uint64_t q_hi = umma_desc_k_sw128(sQ), q_lo = umma_desc_k_sw128(sQ + ATT_TILE);
+        for (int j = 0; j < nkb; ++j) {
+            const int i = j, s = i % ATT_STAGES;
+            mbar_wait(smem_u32(&kv_full[s]), (uint32_t)(i / ATT_STAGES) & 1u);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sk = sKV + s * ATT_SMEM_STAGE;
+                const uint64_t k_hi = umma_desc_k_sw128(sk), k_lo = umma_desc_k_sw128(sk + ATT_TILE);
+                const uint32_t d_s = tmem_base + (uint32_t)(j * ATT_BKEY);
+#pragma unroll
+                for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_hi + 2 * k, k_hi + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_lo + 2 * k, k_hi + 2 * k, idesc_s, 1u);
+#pragma unroll
+                for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_hi + 2 * k, k_lo + 2 * k, idesc_s, 1u);
+                umma_commit(smem_u32(&kv_empty[s]));
+                if (j == nkb - 1) umma_commit(smem_u32(&s_full));
+            }
+            __syncwarp();
+        }
+        const uint64_t p_hi = umma_desc_k_sw128(sP), p_lo = umma_desc_k_sw128(sP + 2 * ATT_TILE);
+        for (int j = 0; j < nkb; ++j) {
+            const int i = nkb + j, s = i % ATT_STAGES;
+            mbar_wait(smem_u32(&kv_full[s]), (uint32_t)(i / ATT_STAGES) & 1u);
+            mbar_wait(smem_u32(&p_full), (uint32_t)j & 1u);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sv = sKV + s * ATT_SMEM_STAGE;
+                const uint64_t v_hi = umma_desc_mn_sw128(sv), v_lo = umma_desc_mn_sw128(sv + ATT_TILE);
+#pragma unroll
+                for (int ks = 0; ks < ATT_BKEY / 16; ++ks) {
+                    // P: k-block (ks/4) of 64 keys is 16 KB further, 32 B per 16-key step inside it; V: 16 rows = 2048 B
+                    const uint64_t pa = (uint64_t)((ks >> 2) * (ATT_TILE >> 4) + (ks & 3) * 2);
+                    const uint64_t va = (uint64_t)(ks * (2048 >> 4));
+                    umma_bf16(tmem_base, p_hi + pa, v_hi + va, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int ks = 0; ks < ATT_BKEY / 16; ++ks) {
+                    const uint64_t pa = (uint64_t)((ks >> 2) * (ATT_TILE >> 4) + (ks & 3) * 2);
+                    const uint64_t va = (uint64_t)(ks * (2048 >> 4));
+                    umma_bf16(tmem_base, p_lo + pa, v_hi + va, idesc_o, 1u);
+                }
+#pragma unroll
+                for (int ks = 0; ks < ATT_BKEY / 16; ++ks) {
+                    const uint64_t pa = (uint64_t)((ks >> 2) * (ATT_TILE >> 4) + (ks & 3) * 2);
+                    const uint64_t va = (uint64_t)(ks * (2048 >> 4));
+                    umma_bf16(tmem_base, p_hi + pa, v_lo + va, idesc_o, 1u);
+                }
+                umma_commit(smem_u32(&kv_empty[s]));
+                umma_commit(smem_u32(&p_empty));
+                if (j == nkb - 1) umma_commit(smem_u32(&o_full));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== softmax / epilogue warps (thread = query row) =====================
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
+        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        mbar_wait(smem_u32(&s_full), 0);
+        tc_fence_after();
+        // ---- pass A: row maximum over all keys -------------------------------------------------
+        float mx = -3.0e38f;
+        for (int j = 0; j < nkb; ++j) {
+#pragma unroll 1
+            for (int c = 0; c < ATT_BKEY / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + (uint32_t)(j * ATT_BKEY + c * 32), v);
+                tmem_ld_wait();
+                const int key0 = j * ATT_BKEY + c * 32;
+#pragma unroll
+                for (int t = 0; t < 32; ++t)
+                    if (key0 + t < p.L) mx = fmaxf(mx, __uint_as_float(v[t]));
+            }
+        }
+        const float mscaled = mx * p.scale_log2e;
+        // ---- pass B: P_j = exp2(s*scale*log2e - m) -> shared memory, row sum -------------------------
+        float lsum = 0.f;
+        for (int j = 0; j < nkb; ++j) {
+            if (j > 0) mbar_wait(smem_u32(&p_empty), (uint32_t)(j - 1) & 1u);  // PV_{j-1} has consumed P
+#pragma unroll 1
+            for (int c = 0; c < ATT_BKEY / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + (uint32_t)(j * ATT_BKEY + c * 32), v);
+                tmem_ld_wait();
+                const int key0 = j * ATT_BKEY + c * 32;
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int t = 0; t < 32; t += 2) {
+                    float e0 = (key0 + t < p.L) ? exp2f(fmaf(__uint_as_float(v[t]), p.scale_log2e, -mscaled)) : 0.f;
+                    float e1 = (key0 + t + 1 < p.L) ? exp2f(fmaf(__uint_as_float(v[t + 1]), p.scale_log2e, -mscaled)) : 0.f;
+                    lsum += e0 + e1;
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(e0, h0, l0);
+                    split_bf16(e1, h1, l1);
+                    hi[t >> 1] = pack_bf16x2(h0, h1);
+                    lo[t >> 1] = pack_bf16x2(l0, l1);
+                }
+                // keys [c*32, c*32+32) of this block: k-block kb = c/2, 16-byte chunks (c&1)*4 .. +3 of row r
+                const uint32_t rowbase = (uint32_t)((c >> 1) * ATT_TILE + r * 128);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint32_t chunk = (uint32_t)(((c & 1) * 4 + q4) ^ (r & 7));
+                    st_shared_v4(sP + rowbase + chunk * 16, hi[q4 * 4], hi[q4 * 4 + 1], hi[q4 * 4 + 2], hi[q4 * 4 + 3]);
+                    st_shared_v4(sP + 2 * ATT_TILE + rowbase + chunk * 16, lo[q4 * 4], lo[q4 * 4 + 1], lo[q4 * 4 + 2], lo[q4 * 4 + 3]);
+                }
+            }
+            tc_fence_before();      // our TMEM reads of S_j are complete before the MMA may overwrite columns
+            fence_proxy_async();    // generic-proxy smem writes -> visible to the async proxy (UMMA)
+            mbar_arrive(smem_u32(&p_full));
+        }
+        // ---- epilogue: O / rowsum -> split-bf16 [B*L, H*dh] --------------------------------------
+        mbar_wait(smem_u32(&o_full), 0);
+        tc_fence_after();
+        const int qrow = q_tile * ATT_BQ + r;
+        const float inv = 1.0f / lsum;
+        __nv_bfloat16* ohi = p.out_hi + (long long)b * p.out_b + (long long)h * p.out_h + (long long)qrow * p.ldo;
+        __nv_bfloat16* olo = ohi + p.out_plane;
+#pragma unroll 1
+        for (int c = 0; c < ATT_DH / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+            if (qrow < p.L) {
+#pragma unroll
+                for (int t = 0; t < 32; t += 8) {
+                    uint32_t hh[4], ll[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        split_bf16(__uint_as_float(v[t + 2 * u]) * inv, h0, l0);
+                        split_bf16(__uint_as_float(v[t + 2 * u + 1]) * inv, h1, l1);
+                        hh[u] = pack_bf16x2(h0, h1);
+                        ll[u] = pack_bf16x2(l0, l1);
+                    }
+                    *reinterpret_cast<uint4*>(ohi + c * 32 + t) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                    *reinterpret_cast<uint4*>(olo + c * 32 + t) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+int make_operand_map_ext(CUtensorMap* map, const psam_operand* op, int box_rows);  // gemm_tc.cu
+
+}  // namespace psam
+
+extern "C" int psam_attention_bf16x3(const psam_operand* q, const psam_operand* k, const psam_operand* v, void* out_hi,
+                                     long long out_plane, long long ldo, long long out_head_stride,
+                                     long long out_cloud_stride, float scale, cudaStream_t stream) {
+    using namespace psam;
+    if (!q || !k || !v || !out_hi) return PSAM_ERR_ARG;
+    const int L = q->rows, dh = q->k;
+    const int H = q->nb1 > 0 ? q->nb1 : 1, B = q->nb2 > 0 ? q->nb2 : 1;
+    if (dh != ATT_DH || L > 512 || L <= 0) return PSAM_ERR_UNSUPPORTED;
+    if (k->rows != L || v->rows != L || k->k != dh || v->k != dh) return PSAM_ERR_ARG;
+    if ((ldo | out_plane | out_head_stride | out_cloud_stride) & 7) return PSAM_ERR_ARG;
+    CUtensorMap mq, mk, mv;
+    int rc = make_operand_map_ext(&mq, q, ATT_BQ);
+    if (rc) return rc;
+    rc = make_operand_map_ext(&mk, k, ATT_BKEY);
+    if (rc) return rc;
+    rc = make_operand_map_ext(&mv, v, ATT_BKEY);
+    if (rc) return rc;
+    AttnParams p;
+    p.L = L, p.H = H, p.B = B;
+    p.scale_log2e = scale * 1.4426950408889634f;
+    p.out_hi = (__nv_bfloat16*)out_hi;
+    p.out_plane = out_plane, p.ldo = ldo, p.out_h = out_head_stride, p.out_b = out_cloud_stride;
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+    dim3 grid((unsigned)ceil_div(L, ATT_BQ), (unsigned)H, (unsigned)B);
+    attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, stream>>>(mq, mk, mv, p);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}

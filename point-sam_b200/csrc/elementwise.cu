@@ -25,68 +25,124 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* hi, long long plane, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm (one warp per row; two-pass mean/variance like F.layer_norm)
+// LayerNorm family.  Values are read ONCE and kept in registers; mean/variance are the two-pass form
+// of F.layer_norm.  Two mappings: one warp per row (many rows) or one CTA per row (few, wide rows -
+// the 512-token ViT stream would otherwise occupy 64 CTAs only).
 // ---------------------------------------------------------------------------------------------
-__global__ void layernorm_kernel(const psam_ln_args a) {
-    const int warps_per_block = blockDim.x >> 5;
-    const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();  // protect `red` from the previous use
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = (l < 8) ? red[l] : 0.f;
+    return warp_sum(t);
+}
+
+__device__ __forceinline__ float ln_input(const psam_ln_args& a, const float* x, const float* r, const float* gb, int c) {
+    float v = x[c];
+    if (r) v += r[c];
+    if (gb) v += gb[c];
+    return v;
+}
+
+__device__ __forceinline__ void ln_store(const psam_ln_args& a, long long row, int c, float v) {
+    v = apply_act(v, a.act);
+    if (a.y) a.y[row * a.ldy + c] = v;
+    if (a.y_hi) store_split((__nv_bfloat16*)a.y_hi, a.y_plane, row * a.ldy_s + c, v);
+}
+
+template <int VPL>  // values per lane, D <= 32*VPL
+__global__ void __launch_bounds__(256) layernorm_warp_kernel(const psam_ln_args a) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= a.rows) return;
     const float* x = a.x + row * a.ldx;
     const float* r = a.r ? a.r + row * a.ldr : nullptr;
     const float* gb = a.gbias ? a.gbias + (row / a.group_rows) * a.ld_gbias : nullptr;
-    auto val = [&](int c) {
-        float v = x[c];
-        if (r) v += r[c];
-        if (gb) v += gb[c];
-        return v;
-    };
+    float v[VPL];
     float s = 0.f;
-    for (int c = lane; c < a.D; c += 32) s += val(c);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = c < a.D ? ln_input(a, x, r, gb, c) : 0.f;
+        s += v[i];
+    }
     const float mean = warp_sum(s) / (float)a.D;
     float q = 0.f;
-    for (int c = lane; c < a.D; c += 32) {
-        const float d = val(c) - mean;
-        q += d * d;
-    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+        if (lane + 32 * i < a.D) q += (v[i] - mean) * (v[i] - mean);
     const float rstd = rsqrtf(warp_sum(q) / (float)a.D + a.eps);
-    __nv_bfloat16* yh = (__nv_bfloat16*)a.y_hi;
-    for (int c = lane; c < a.D; c += 32) {
-        float v = (val(c) - mean) * rstd * a.gamma[c] + a.beta[c];
-        v = apply_act(v, a.act);
-        if (a.y) a.y[row * a.ldy + c] = v;
-        if (yh) store_split(yh, a.y_plane, row * a.ldy_s + c, v);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int c = lane + 32 * i;
+        if (c < a.D) ln_store(a, row, c, (v[i] - mean) * rstd * a.gamma[c] + a.beta[c]);
     }
-    if (yh)
-        for (int c = a.D + lane; c < a.pitch; c += 32) {
-            yh[row * a.ldy_s + c] = __float2bfloat16_rn(0.f);
-            yh[row * a.ldy_s + c + a.y_plane] = __float2bfloat16_rn(0.f);
-        }
+    if (a.y_hi)
+        for (int c = a.D + lane; c < a.pitch; c += 32) store_split((__nv_bfloat16*)a.y_hi, a.y_plane, row * a.ldy_s + c, 0.f);
 }
 
-__global__ void swiglu_ln_kernel(const float* __restrict__ gx, long long ld, long long x_off, int rows, int H,
-                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                 __nv_bfloat16* __restrict__ yh, long long y_plane, long long ldy_s, long long pitch) {
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
+template <int VPT>  // values per thread, D <= 256*VPT
+__global__ void __launch_bounds__(256) layernorm_block_kernel(const psam_ln_args a) {
+    __shared__ float red[8];
+    const long long row = blockIdx.x;
+    const float* x = a.x + row * a.ldx;
+    const float* r = a.r ? a.r + row * a.ldr : nullptr;
+    const float* gb = a.gbias ? a.gbias + (row / a.group_rows) * a.ld_gbias : nullptr;
+    float v[VPT];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        v[i] = c < a.D ? ln_input(a, x, r, gb, c) : 0.f;
+        s += v[i];
+    }
+    const float mean = block_sum_256(s, red) / (float)a.D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+        if (threadIdx.x + 256 * i < a.D) q += (v[i] - mean) * (v[i] - mean);
+    const float rstd = rsqrtf(block_sum_256(q, red) / (float)a.D + a.eps);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        if (c < a.D) ln_store(a, row, c, (v[i] - mean) * rstd * a.gamma[c] + a.beta[c]);
+    }
+    if (a.y_hi)
+        for (int c = a.D + threadIdx.x; c < a.pitch; c += 256) store_split((__nv_bfloat16*)a.y_hi, a.y_plane, row * a.ldy_s + c, 0.f);
+}
+
+// SwiGLU + inner LayerNorm, one CTA per row, h = silu(g)*x computed once and kept in registers.
+template <int VPT>
+__global__ void __launch_bounds__(256)
+swiglu_ln_kernel(const float* __restrict__ gx, long long ld, long long x_off, int rows, int H, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ yh, long long y_plane, long long ldy_s,
+                 long long pitch) {
+    __shared__ float red[8];
+    const long long row = blockIdx.x;
     const float* g = gx + row * ld;
     const float* x = g + x_off;
-    auto val = [&](int c) { return silu(g[c]) * x[c]; };
+    float v[VPT];
     float s = 0.f;
-    for (int c = lane; c < H; c += 32) s += val(c);
-    const float mean = warp_sum(s) / (float)H;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        v[i] = c < H ? silu(g[c]) * x[c] : 0.f;
+        s += v[i];
+    }
+    const float mean = block_sum_256(s, red) / (float)H;
     float q = 0.f;
-    for (int c = lane; c < H; c += 32) {
-        const float d = val(c) - mean;
-        q += d * d;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+        if (threadIdx.x + 256 * i < H) q += (v[i] - mean) * (v[i] - mean);
+    const float rstd = rsqrtf(block_sum_256(q, red) / (float)H + eps);
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+        const int c = threadIdx.x + 256 * i;
+        if (c < H) store_split(yh, y_plane, row * ldy_s + c, (v[i] - mean) * rstd * gamma[c] + beta[c]);
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)H + eps);
-    for (int c = lane; c < H; c += 32) store_split(yh, y_plane, row * ldy_s + c, (val(c) - mean) * rstd * gamma[c] + beta[c]);
-    for (int c = H + lane; c < pitch; c += 32) {
-        yh[row * ldy_s + c] = __float2bfloat16_rn(0.f);
-        yh[row * ldy_s + c + y_plane] = __float2bfloat16_rn(0.f);
-    }
+    for (int c = H + threadIdx.x; c < pitch; c += 256) store_split(yh, y_plane, row * ldy_s + c, 0.f);
 }
 
 // y = act(LN?(x W^T + b)); Cin <= 8; one warp per row, lane owns outputs lane, lane+32, ...
@@ -215,46 +271,54 @@ __global__ void posenc_kernel(const float* __restrict__ coords, long long rows, 
     }
 }
 
-// one warp per (z, head, query); scores kept in shared memory (Lk <= 4096)
+// one warp per (z, head, query); scores kept in shared memory (Lk <= 4096).  Both phases split the KEYS across
+// lanes (the value phase accumulates dh partial sums per lane and reduces them with shuffles), so long
+// key sequences (tokens -> 512 patches) do not serialise on one lane.
+template <int DH>
 __global__ void attention_small_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                                       float* __restrict__ o, int Z, int Lq, int Lk, int H, int dh, long long ldq, long long ldk,
+                                       float* __restrict__ o, int Z, int Lq, int Lk, int H, long long ldq, long long ldk,
                                        long long ldv, long long ldo) {
-    extern __shared__ float s_sc[];  // [warps][Lk] + [warps][dh] query
+    extern __shared__ float s_sc[];  // [warps][Lk] + [warps][DH] query
     const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long item = (long long)blockIdx.x * wpb + w;
     if (item >= (long long)Z * H * Lq) return;
     const int i = (int)(item % Lq);
     const int h = (int)((item / Lq) % H);
     const int z = (int)(item / ((long long)Lq * H));
-    float* sc = s_sc + (size_t)w * (Lk + dh);
+    float* sc = s_sc + (size_t)w * (Lk + DH);
     float* sq = sc + Lk;
-    const float* qp = q + ((long long)z * Lq + i) * ldq + h * dh;
-    for (int d = lane; d < dh; d += 32) sq[d] = qp[d];
+    const float* qp = q + ((long long)z * Lq + i) * ldq + h * DH;
+    for (int d = lane; d < DH; d += 32) sq[d] = qp[d];
     __syncwarp();
-    const float scale = rsqrtf((float)dh);
+    const float scale = rsqrtf((float)DH);
     float m = -3.4e38f;
     for (int j = lane; j < Lk; j += 32) {
-        const float* kp = k + ((long long)z * Lk + j) * ldk + h * dh;
+        const float* kp = k + ((long long)z * Lk + j) * ldk + h * DH;
         float acc = 0.f;
-        for (int d = 0; d < dh; ++d) acc = fmaf(sq[d], kp[d], acc);
+#pragma unroll
+        for (int d = 0; d < DH; ++d) acc = fmaf(sq[d], kp[d], acc);
         acc *= scale;
         sc[j] = acc;
         m = fmaxf(m, acc);
     }
     m = warp_max(m);
     float sum = 0.f;
+    float acc[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = 0.f;
     for (int j = lane; j < Lk; j += 32) {
         const float e = __expf(sc[j] - m);
-        sc[j] = e;
         sum += e;
+        const float* vp = v + ((long long)z * Lk + j) * ldv + h * DH;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) acc[d] = fmaf(e, vp[d], acc[d]);
     }
     const float inv = 1.0f / warp_sum(sum);
-    __syncwarp();
-    float* op = o + ((long long)z * Lq + i) * ldo + h * dh;
-    for (int d = lane; d < dh; d += 32) {
-        float acc = 0.f;
-        for (int j = 0; j < Lk; ++j) acc = fmaf(sc[j], v[((long long)z * Lk + j) * ldv + h * dh + d], acc);
-        op[d] = acc * inv;
+    float* op = o + ((long long)z * Lq + i) * ldo + h * DH;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) {
+        const float t = warp_sum(acc[d]);
+        if (lane == (d & 31)) op[d] = t * inv;
     }
 }
 
@@ -425,6 +489,109 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const psam_linear_args 
         }
 }
 
+
+// fp32 SIMT linear for mid-size M (keys side of the decoder): 32x64 tile, BK=32, float4 loads along K,
+// all loads of a k-step in flight before the barrier.  Requires K%4==0, ldx%4==0, ldw%4==0.
+__global__ void __launch_bounds__(256) linear_f32_v4_kernel(const psam_linear_args a) {
+    __shared__ float sx[32][33];
+    __shared__ float sw[32][65];
+    const int z = blockIdx.z;
+    const float* x = a.x + z * a.x_z;
+    const float* x2 = a.x2 ? a.x2 + z * a.x2_z : nullptr;
+    const float* w = a.w + z * a.w_z;
+    const float* b = a.b ? a.b + z * a.b_z : nullptr;
+    const float* r = a.r ? a.r + z * a.r_z : nullptr;
+    float* y = a.y + z * a.y_z;
+    const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, each 2 (m) x 4 (n)
+    const int lr = threadIdx.x >> 3, lk = (threadIdx.x & 7) * 4;  // loader: row 0..31, k offset 0..28
+    float acc[2][4] = {};
+    for (int k0 = 0; k0 < a.K; k0 += 32) {
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), w0 = xv, w1 = xv;
+        const int k = k0 + lk;
+        if (k < a.K) {
+            if (m0 + lr < a.M) {
+                xv = *reinterpret_cast<const float4*>(x + (long long)(m0 + lr) * a.ldx + k);
+                if (x2) {
+                    const float4 t = *reinterpret_cast<const float4*>(x2 + (long long)(m0 + lr) * a.ldx + k);
+                    xv.x += t.x, xv.y += t.y, xv.z += t.z, xv.w += t.w;
+                }
+            }
+            if (n0 + lr < a.N) w0 = *reinterpret_cast<const float4*>(w + (long long)(n0 + lr) * a.ldw + k);
+            if (n0 + 32 + lr < a.N) w1 = *reinterpret_cast<const float4*>(w + (long long)(n0 + 32 + lr) * a.ldw + k);
+        }
+        __syncthreads();
+        sx[lk][lr] = xv.x, sx[lk + 1][lr] = xv.y, sx[lk + 2][lr] = xv.z, sx[lk + 3][lr] = xv.w;
+        sw[lk][lr] = w0.x, sw[lk + 1][lr] = w0.y, sw[lk + 2][lr] = w0.z, sw[lk + 3][lr] = w0.w;
+        sw[lk][lr + 32] = w1.x, sw[lk + 1][lr + 32] = w1.y, sw[lk + 2][lr + 32] = w1.z, sw[lk + 3][lr + 32] = w1.w;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 32; ++kk) {
+            const float xa0 = sx[kk][ty * 2], xa1 = sx[kk][ty * 2 + 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float wb = sw[kk][tx + 16 * j];
+                acc[0][j] = fmaf(xa0, wb, acc[0][j]);
+                acc[1][j] = fmaf(xa1, wb, acc[1][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + ty * 2 + i, n = n0 + tx + 16 * j;
+            if (m < a.M && n < a.N) {
+                float v = acc[i][j];
+                if (b) v += b[n];
+                v = apply_act(v, a.act);
+                if (r) v += r[(long long)m * a.ldy + n];
+                y[(long long)m * a.ldy + n] = v;
+            }
+        }
+}
+
+// Small-M fp32 linear (M <= 16): one warp per output column, lanes stride over K (coalesced weight
+// reads), all M rows accumulated at once.  The token side of the prompt decoder is all of this shape.
+template <int MR>
+__global__ void __launch_bounds__(256) linear_gemv_kernel(const psam_linear_args a) {
+    const int z = blockIdx.y;
+    const float* x = a.x + z * a.x_z;
+    const float* x2 = a.x2 ? a.x2 + z * a.x2_z : nullptr;
+    const float* w = a.w + z * a.w_z;
+    const float* b = a.b ? a.b + z * a.b_z : nullptr;
+    const float* r = a.r ? a.r + z * a.r_z : nullptr;
+    float* y = a.y + z * a.y_z;
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (n >= a.N) return;
+    const float* wr = w + (long long)n * a.ldw;
+    float acc[MR];
+#pragma unroll
+    for (int m = 0; m < MR; ++m) acc[m] = 0.f;
+    for (int k = lane; k < a.K; k += 32) {
+        const float wv = wr[k];
+#pragma unroll
+        for (int m = 0; m < MR; ++m)
+            if (m < a.M) {
+                float xv = x[(long long)m * a.ldx + k];
+                if (x2) xv += x2[(long long)m * a.ldx + k];
+                acc[m] = fmaf(xv, wv, acc[m]);
+            }
+    }
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+        const float t = warp_sum(acc[m]);
+        if (lane == 0 && m < a.M) {
+            float v = t;
+            if (b) v += b[n];
+            v = apply_act(v, a.act);
+            if (r) v += r[(long long)m * a.ldy + n];
+            y[(long long)m * a.ldy + n] = v;
+        }
+    }
+}
+
 static inline int grid_for(long long work, int per_block, int max_blocks = 148 * 32) {
     long long g = (work + per_block - 1) / per_block;
     if (g < 1) g = 1;
@@ -439,7 +606,23 @@ using namespace psam;
 extern "C" int psam_layernorm_f32(const psam_ln_args* a, cudaStream_t stream) {
     if (!a || !a->x || !a->gamma || !a->beta || a->rows <= 0 || a->D <= 0 || (!a->y && !a->y_hi)) return PSAM_ERR_ARG;
     if (a->gbias && a->group_rows <= 0) return PSAM_ERR_ARG;
-    layernorm_kernel<<<ceil_div(a->rows, 8), 256, 0, stream>>>(*a);
+    if (a->D > 4096) return PSAM_ERR_UNSUPPORTED;
+    const bool block_per_row = (a->D > 1024) || (a->D >= 256 && a->rows <= 8192);
+    if (block_per_row) {
+        const int vpt = ceil_div(a->D, 256);
+        if (vpt <= 1) layernorm_block_kernel<1><<<a->rows, 256, 0, stream>>>(*a);
+        else if (vpt <= 2) layernorm_block_kernel<2><<<a->rows, 256, 0, stream>>>(*a);
+        else if (vpt <= 4) layernorm_block_kernel<4><<<a->rows, 256, 0, stream>>>(*a);
+        else if (vpt <= 8) layernorm_block_kernel<8><<<a->rows, 256, 0, stream>>>(*a);
+        else layernorm_block_kernel<16><<<a->rows, 256, 0, stream>>>(*a);
+    } else {
+        const int vpl = ceil_div(a->D, 32);
+        const int blocks = ceil_div(a->rows, 8);
+        if (vpl <= 4) layernorm_warp_kernel<4><<<blocks, 256, 0, stream>>>(*a);
+        else if (vpl <= 8) layernorm_warp_kernel<8><<<blocks, 256, 0, stream>>>(*a);
+        else if (vpl <= 16) layernorm_warp_kernel<16><<<blocks, 256, 0, stream>>>(*a);
+        else layernorm_warp_kernel<32><<<blocks, 256, 0, stream>>>(*a);
+    }
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -448,8 +631,18 @@ extern "C" int psam_swiglu_ln(const float* gx, long long ld, long long x_off, in
                               const float* beta, float eps, void* y_hi, long long y_plane, long long ldy_s, long long pitch,
                               cudaStream_t stream) {
     if (!gx || !gamma || !beta || !y_hi || rows <= 0 || H <= 0 || pitch < H) return PSAM_ERR_ARG;
-    swiglu_ln_kernel<<<ceil_div(rows, 8), 256, 0, stream>>>(gx, ld, x_off, rows, H, gamma, beta, eps, (__nv_bfloat16*)y_hi,
-                                                            y_plane, ldy_s, pitch);
+    if (H > 8192) return PSAM_ERR_UNSUPPORTED;
+    __nv_bfloat16* yh = (__nv_bfloat16*)y_hi;
+    const int vpt = ceil_div(H, 256);
+#define PSAM_SWI(V) swiglu_ln_kernel<V><<<rows, 256, 0, stream>>>(gx, ld, x_off, rows, H, gamma, beta, eps, yh, y_plane, ldy_s, pitch)
+    if (vpt <= 2) PSAM_SWI(2);
+    else if (vpt <= 4) PSAM_SWI(4);
+    else if (vpt <= 8) PSAM_SWI(8);
+    else if (vpt <= 12) PSAM_SWI(12);
+    else if (vpt <= 16) PSAM_SWI(16);
+    else if (vpt <= 24) PSAM_SWI(24);
+    else PSAM_SWI(32);
+#undef PSAM_SWI
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -521,10 +714,19 @@ extern "C" int psam_attention_f32(const float* q, const float* k, const float* v
     const int wpb = 4;
     const size_t smem = (size_t)wpb * (Lk + dh) * sizeof(float);
     if (smem > 200 * 1024) return PSAM_ERR_UNSUPPORTED;
-    PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long items = (long long)Z * H * Lq;
-    attention_small_kernel<<<(unsigned)ceil_div_ll(items, wpb), wpb * 32, smem, stream>>>(q, k, v, o, Z, Lq, Lk, H, dh, ldq, ldk,
-                                                                                         ldv, ldo);
+    const unsigned grid = (unsigned)ceil_div_ll(items, wpb);
+#define PSAM_ATT(DH)                                                                                                        \
+    {                                                                                                                       \
+        PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_small_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        attention_small_kernel<DH><<<grid, wpb * 32, smem, stream>>>(q, k, v, o, Z, Lq, Lk, H, ldq, ldk, ldv, ldo);         \
+    }
+    if (dh == 16) PSAM_ATT(16)
+    else if (dh == 32) PSAM_ATT(32)
+    else if (dh == 64) PSAM_ATT(64)
+    else if (dh == 8) PSAM_ATT(8)
+    else return PSAM_ERR_UNSUPPORTED;
+#undef PSAM_ATT
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -578,8 +780,20 @@ extern "C" int psam_split_f32(const float* x, long long ld, long long rows, int 
 
 extern "C" int psam_linear_f32(const psam_linear_args* a, cudaStream_t stream) {
     if (!a || !a->x || !a->w || !a->y || a->M <= 0 || a->N <= 0 || a->K <= 0 || a->Z <= 0) return PSAM_ERR_ARG;
-    dim3 grid(ceil_div(a->N, 64), ceil_div(a->M, 64), a->Z);
-    linear_f32_kernel<<<grid, 256, 0, stream>>>(*a);
+    if (a->M <= 16) {
+        dim3 grid(ceil_div(a->N, 8), a->Z);
+        if (a->M <= 1) linear_gemv_kernel<1><<<grid, 256, 0, stream>>>(*a);
+        else if (a->M <= 4) linear_gemv_kernel<4><<<grid, 256, 0, stream>>>(*a);
+        else if (a->M <= 8) linear_gemv_kernel<8><<<grid, 256, 0, stream>>>(*a);
+        else linear_gemv_kernel<16><<<grid, 256, 0, stream>>>(*a);
+    } else if (a->K % 4 == 0 && a->ldx % 4 == 0 && a->ldw % 4 == 0 && ((uintptr_t)a->x % 16) == 0 && ((uintptr_t)a->w % 16) == 0 &&
+               (!a->x2 || (uintptr_t)a->x2 % 16 == 0) && a->x_z % 4 == 0 && a->w_z % 4 == 0 && a->x2_z % 4 == 0) {
+        dim3 grid(ceil_div(a->N, 64), ceil_div(a->M, 32), a->Z);
+        linear_f32_v4_kernel<<<grid, 256, 0, stream>>>(*a);
+    } else {
+        dim3 grid(ceil_div(a->N, 64), ceil_div(a->M, 64), a->Z);
+        linear_f32_kernel<<<grid, 256, 0, stream>>>(*a);
+    }
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }

@@ -6,11 +6,12 @@
 //
 // Design: one thread-block CLUSTER per cloud.  The cloud (xyz + running min-distance) lives in the
 // registers of the cluster's threads for the whole kernel, so an iteration touches no global memory.
-// Per iteration every warp reduces its candidates with redux.sync, publishes one 20-byte record
-// (max-distance bits, tie-break priority, xyz of the candidate) into the shared memory of EVERY CTA
-// of the cluster (DSMEM store) and signals that CTA's mbarrier (remote arrive, release.cluster); all
-// threads then wait on their local mbarrier (acquire.cluster) and reduce the C*W records.  There is
-// no __syncthreads and no barrier.cluster in the loop - one DSMEM hop per iteration.
+// Per iteration every warp reduces its candidates with redux.sync into one 20-byte record (max-distance
+// bits, tie-break priority, xyz of the candidate); the CTA combines its warps' records through shared
+// memory (one __syncthreads) and warp 0 pushes the CTA record into the shared memory of EVERY CTA of the
+// cluster with st.async (DSMEM store that completes transaction bytes on the receiver's mbarrier - data
+// and signal in a single hop).  All threads then wait on their local mbarrier and reduce the C records.
+// No barrier.cluster inside the loop.
 //
 // Bit-exactness: squared distance is fmaf(dz,dz,fmaf(dy,dy,dx*dx)) with d = p_j - p_sel, and among
 // equal maxima the winner is the lexicographic minimum of (bitrev(j mod T), j div T), T = the
@@ -42,19 +43,21 @@ template <int PPT>
 __global__ void __launch_bounds__(FPS_THREADS, 1)
 fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long long* __restrict__ idx_out,
                    float* __restrict__ centers_out, float* __restrict__ ws) {
-    __shared__ __align__(16) uint4 slot_a[2][FPS_MAX_SLOTS];  // {dist bits, prio, x, y}
-    __shared__ float slot_z[2][FPS_MAX_SLOTS];
+    __shared__ __align__(16) uint4 slot_a[2][FPS_MAX_CLUSTER];  // records received from the cluster {bits, prio, x, y}
+    __shared__ float slot_z[2][FPS_MAX_CLUSTER];
+    __shared__ __align__(16) uint4 wrec_a[2][FPS_WARPS];        // per-warp records of this CTA
+    __shared__ float wrec_z[2][FPS_WARPS];
     __shared__ __align__(8) uint64_t mbar[2];
 
     const uint32_t C = cluster_nctarank();
     const uint32_t rank = cluster_ctarank();
     const int cloud = blockIdx.x / C;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t nslots = C * FPS_WARPS;
     const uint32_t tmask = (1u << log2T) - 1u;
-    const uint32_t qmask = (log2T == 32) ? 0u : ((1u << (32 - log2T)) - 1u);
+    const uint32_t qmask = (1u << (32 - log2T)) - 1u;
     const int stride = (int)C * FPS_THREADS;
     const int gt = (int)rank * FPS_THREADS + tid;
+    const uint32_t tx_bytes = C * 20u;  // every peer (incl. this CTA) delivers 16 + 4 bytes per iteration
 
     xyz += (size_t)cloud * N * 3;
     idx_out += (size_t)cloud * G;
@@ -62,9 +65,11 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long 
     float* md_g = (PPT == 0) ? ws + (size_t)cloud * N : nullptr;
 
     if (tid == 0) {
-        mbar_init(smem_u32(&mbar[0]), nslots);
-        mbar_init(smem_u32(&mbar[1]), nslots);
+        mbar_init(smem_u32(&mbar[0]), 1);
+        mbar_init(smem_u32(&mbar[1]), 1);
         fence_mbar_init();
+        mbar_arrive_expect_tx(smem_u32(&mbar[0]), tx_bytes);  // armed for iterations 2 and 1
+        mbar_arrive_expect_tx(smem_u32(&mbar[1]), tx_bytes);
     }
 
     float px[PPT > 0 ? PPT : 1], py[PPT > 0 ? PPT : 1], pz[PPT > 0 ? PPT : 1], md[PPT > 0 ? PPT : 1];
@@ -94,7 +99,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long 
         centers_out[1] = cy;
         centers_out[2] = cz;
     }
-    cluster_sync_all();  // barriers initialised everywhere before the first remote arrive
+    cluster_sync_all();  // barriers initialised and armed everywhere before the first remote store
 
     for (int it = 1; it < G; ++it) {
         const int p = it & 1;
@@ -140,49 +145,56 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long 
             if (bestbits != wmax) myprio = 0xFFFFFFFFu;
         }
         const uint32_t wprio = __reduce_min_sync(0xffffffffu, myprio);
-        const uint32_t owner_mask = __ballot_sync(0xffffffffu, myprio == wprio && bestbits == wmax);
-        const int owner = __ffs(owner_mask) - 1;
-        const float ox = __shfl_sync(0xffffffffu, wx, owner);
-        const float oy = __shfl_sync(0xffffffffu, wy, owner);
-        const float oz = __shfl_sync(0xffffffffu, wz, owner);
-        // ---- 3. publish to every CTA of the cluster (lane c serves peer c) --------------------
-        if ((uint32_t)lane < C) {
-            const uint32_t slot = rank * FPS_WARPS + warp;
-            const uint32_t ra = mapa_shared(smem_u32(&slot_a[p][slot]), lane);
-            const uint32_t rz = mapa_shared(smem_u32(&slot_z[p][slot]), lane);
-            const uint32_t rb = mapa_shared(smem_u32(&mbar[p]), lane);
-            st_cluster_v4(ra, wmax, wprio, __float_as_uint(ox), __float_as_uint(oy));
-            st_cluster_u32(rz, __float_as_uint(oz));
-            mbar_arrive_remote_release(rb);
+        if (myprio == wprio && bestbits == wmax) {  // exactly one lane (priorities are unique per point)
+            wrec_a[p][warp] = make_uint4(wmax, wprio, __float_as_uint(wx), __float_as_uint(wy));
+            wrec_z[p][warp] = wz;
         }
-        // ---- 4. wait for all C*W records of this iteration ------------------------------------
+        __syncthreads();
+        // ---- 3. warp 0: CTA record -> every CTA of the cluster (st.async, lane c serves peer c) --
+        if (warp == 0) {
+            uint4 a = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);
+            float z = 0.f;
+            if (lane < FPS_WARPS) {
+                a = wrec_a[p][lane];
+                z = wrec_z[p][lane];
+            }
+            const uint32_t cmax = __reduce_max_sync(0xffffffffu, a.x);
+            const uint32_t cprio = __reduce_min_sync(0xffffffffu, a.x == cmax ? a.y : 0xFFFFFFFFu);
+            const int src = __ffs(__ballot_sync(0xffffffffu, a.x == cmax && a.y == cprio)) - 1;
+            const uint32_t ox = __shfl_sync(0xffffffffu, a.z, src);
+            const uint32_t oy = __shfl_sync(0xffffffffu, a.w, src);
+            const uint32_t oz = __shfl_sync(0xffffffffu, __float_as_uint(z), src);
+            if ((uint32_t)lane < C) {
+                const uint32_t ra = mapa_shared(smem_u32(&slot_a[p][rank]), lane);
+                const uint32_t rz = mapa_shared(smem_u32(&slot_z[p][rank]), lane);
+                const uint32_t rb = mapa_shared(smem_u32(&mbar[p]), lane);
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                             ::"r"(ra), "r"(cmax), "r"(cprio), "r"(ox), "r"(oy), "r"(rb) : "memory");
+                asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                             ::"r"(rz), "r"(oz), "r"(rb) : "memory");
+            }
+        }
+        // ---- 4. wait for the C records of this iteration, re-arm the barrier for iteration it+2 ----
         {
             const uint32_t bar = smem_u32(&mbar[p]);
             const uint32_t parity = ((uint32_t)(it - 1) >> 1) & 1u;
             while (!mbar_try_wait_acquire_cluster(bar, parity)) {
             }
+            if (tid == 0) mbar_arrive_expect_tx(bar, tx_bytes);
         }
         // ---- 5. reduce the records (every warp redundantly) -----------------------------------
-        uint32_t gbits = 0, gprio = 0xFFFFFFFFu;
-        float gx = 0.f, gy = 0.f, gz = 0.f;
-        for (uint32_t s = lane; s < nslots; s += 32) {
-            const uint4 a = slot_a[p][s];
-            const float z = slot_z[p][s];
-            if (a.x > gbits || (a.x == gbits && a.y < gprio)) {
-                gbits = a.x;
-                gprio = a.y;
-                gx = __uint_as_float(a.z);
-                gy = __uint_as_float(a.w);
-                gz = z;
-            }
+        uint4 a = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);
+        float z = 0.f;
+        if ((uint32_t)lane < C) {
+            a = slot_a[p][lane];
+            z = slot_z[p][lane];
         }
-        const uint32_t fmax = __reduce_max_sync(0xffffffffu, gbits);
-        const uint32_t fprio = __reduce_min_sync(0xffffffffu, gbits == fmax ? gprio : 0xFFFFFFFFu);
-        const uint32_t fmask = __ballot_sync(0xffffffffu, gbits == fmax && gprio == fprio);
-        const int fo = __ffs(fmask) - 1;
-        const float nx = __shfl_sync(0xffffffffu, gx, fo);
-        const float ny = __shfl_sync(0xffffffffu, gy, fo);
-        const float nz = __shfl_sync(0xffffffffu, gz, fo);
+        const uint32_t fmax = __reduce_max_sync(0xffffffffu, a.x);
+        const uint32_t fprio = __reduce_min_sync(0xffffffffu, a.x == fmax ? a.y : 0xFFFFFFFFu);
+        const int fo = __ffs(__ballot_sync(0xffffffffu, a.x == fmax && a.y == fprio)) - 1;
+        const float nx = __uint_as_float(__shfl_sync(0xffffffffu, a.z, fo));
+        const float ny = __uint_as_float(__shfl_sync(0xffffffffu, a.w, fo));
+        const float nz = __shfl_sync(0xffffffffu, z, fo);
         if (fmax != 0u) {  // max == 0: every remaining point coincides with a selected one -> repeat
             cx = nx, cy = ny, cz = nz;
             sel = ((fprio & qmask) << log2T) | (__brev(fprio & ~qmask));

@@ -15,8 +15,13 @@
 //              64 bf16 x {128|BN} rows, 3-stage mbarrier ring, hi and lo planes of A and W per stage
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128xBNx16, kind::f16),
 //              tcgen05.commit releases smem stages and finally signals the epilogue
-//   warps 2-5: epilogue - tcgen05.ld 32x32b (each warp owns the TMEM lane quarter warp_id % 4),
+//   warps 2-5: epilogue - tcgen05.ld 32x32b (each warp owns the TMEM lane quarter warp_id % 4), per-warp
+//              shared-memory transpose so that every global access is a contiguous row segment,
 //              bias/activation/residual, fp32 and/or split-bf16 stores (red.add for split-K)
+// The output-tile width BN is a runtime multiple of 32 (UMMA N and the TMA box follow it) chosen so the
+// tile count fits the 148 SMs in as few waves as possible.
+#include <stdlib.h>
+
 #include "psam_common.cuh"
 #include "../../include/psam_b200.h"
 
@@ -24,7 +29,6 @@ namespace psam {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_STAGES = 3;
 constexpr int GEMM_THREADS = 192;
 
 struct GemmEpilogue {
@@ -45,34 +49,101 @@ struct GemmShape {
     int nb1, nb2;  // batch extents (blockIdx.z = ((b2 * nb1) + b1) * split_k + split)
     int split_k;
     int passes;  // 1 or 3
+    int bn;      // output-tile width actually used (multiple of 32, <= MAXBN)
 };
 
-template <int BN>
+template <int MAXBN, int STAGES>
 struct GemmSmem {
     static constexpr int A_TILE = GEMM_BM * GEMM_BK * 2;  // bytes per plane
-    static constexpr int B_TILE = BN * GEMM_BK * 2;
+    static constexpr int B_TILE = MAXBN * GEMM_BK * 2;
     static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-    static constexpr int TOTAL = GEMM_STAGES * STAGE + 1024;  // + alignment slack
+    static constexpr int TOTAL = STAGES * STAGE + 1024;  // + alignment slack
+    static constexpr int TMEM_COLS = MAXBN <= 64 ? 64 : (MAXBN <= 128 ? 128 : 256);
 };
 
-template <int BN>
+
+// ---- epilogue row loops, specialised at compile time (runtime flags inside the loop cost ~10 uniform
+//      branches per row and made the epilogue the slowest part of small-K GEMMs) -------------------------
+template <int ACT, bool RES, bool ACC>
+__device__ __forceinline__ void epi_rows_f32(const float* __restrict__ stg, int lane, int row0, int M, int col, bool col_ok,
+                                             float alpha, float bv, float* out, const float* res, long long ldo) {
+    if (!col_ok) return;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+        const int row = row0 + r;
+        if (row < M) {
+            float x = fmaf(stg[r * 33 + lane], alpha, bv);
+            if (RES) x += res[(long long)row * ldo + col];
+            x = apply_act(x, ACT);
+            if (ACC) atomicAdd(out + (long long)row * ldo + col, x);
+            else out[(long long)row * ldo + col] = x;
+        }
+    }
+}
+
+template <int ACT, bool RES, bool F32>
+__device__ __forceinline__ void epi_rows_split(const float* __restrict__ stg, int lane, int row0, int M, int N, int col0,
+                                               float alpha, const float* bias, float* out, const float* res, long long ldo,
+                                               __nv_bfloat16* ohi, long long out_plane, long long ldo_s, bool vec_align) {
+    // lanes 0..15 take row r, lanes 16..31 row r+1, two adjacent columns each
+    const int half = lane >> 4, cpair = (lane & 15) * 2;
+    const int c0 = col0 + cpair;
+    const bool ok0 = c0 < N, ok1 = c0 + 1 < N;
+    const float bv0 = (bias && ok0) ? bias[c0] : 0.f;
+    const float bv1 = (bias && ok1) ? bias[c0 + 1] : 0.f;
+    __nv_bfloat16* olo = ohi + out_plane;
+    const bool vec_ok = vec_align && ok1;
+#pragma unroll 4
+    for (int r = 0; r < 32; r += 2) {
+        const int row = row0 + r + half;
+        if (row < M) {
+            float x0 = fmaf(stg[(r + half) * 33 + cpair], alpha, bv0);
+            float x1 = fmaf(stg[(r + half) * 33 + cpair + 1], alpha, bv1);
+            if (RES) {
+                if (ok0) x0 += res[(long long)row * ldo + c0];
+                if (ok1) x1 += res[(long long)row * ldo + c0 + 1];
+            }
+            x0 = apply_act(x0, ACT);
+            x1 = apply_act(x1, ACT);
+            if (F32) {
+                if (ok0) out[(long long)row * ldo + c0] = x0;
+                if (ok1) out[(long long)row * ldo + c0 + 1] = x1;
+            }
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(x0, h0, l0);
+            split_bf16(x1, h1, l1);
+            const long long o = (long long)row * ldo_s + c0;
+            if (vec_ok) {
+                *reinterpret_cast<uint32_t*>(ohi + o) = pack_bf16x2(h0, h1);
+                *reinterpret_cast<uint32_t*>(olo + o) = pack_bf16x2(l0, l1);
+            } else {
+                if (ok0) ohi[o] = h0, olo[o] = l0;
+                if (ok1) ohi[o + 1] = h1, olo[o + 1] = l1;
+            }
+        }
+    }
+}
+
+template <int MAXBN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmShape shape, const GemmEpilogue ep) {
-    using S = GemmSmem<BN>;
+    using S = GemmSmem<MAXBN, STAGES>;
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t full_bar[GEMM_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[GEMM_STAGES];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
     __shared__ __align__(8) uint64_t tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
 
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x, m_tile = blockIdx.y;
     const int z = blockIdx.z;
     const int split = z % shape.split_k;
     const int bz = z / shape.split_k;
     const int b1 = bz % shape.nb1, b2 = bz / shape.nb1;
+    const int BN = shape.bn;
 
     const int kb_total = (shape.K + GEMM_BK - 1) / GEMM_BK;
     const int kb_per = (kb_total + shape.split_k - 1) / shape.split_k;
@@ -84,14 +155,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        for (int s = 0; s < GEMM_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         mbar_init(smem_u32(&tmem_full_bar), 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), BN);
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), S::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -100,10 +171,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const uint32_t stage_bytes = (lo_pass ? 2u : 1u) * (uint32_t)(S::A_TILE + S::B_TILE);
+            const uint32_t stage_bytes = (lo_pass ? 2u : 1u) * (uint32_t)(S::A_TILE + BN * GEMM_BK * 2);
             for (int i = 0; i < num_kb; ++i) {
-                const int s = i % GEMM_STAGES;
-                const uint32_t ph = (uint32_t)(i / GEMM_STAGES) & 1u;
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
                 const uint32_t fb = smem_u32(&full_bar[s]);
                 mbar_arrive_expect_tx(fb, stage_bytes);
@@ -119,10 +190,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+        const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
         for (int i = 0; i < num_kb; ++i) {
-            const int s = i % GEMM_STAGES;
-            const uint32_t ph = (uint32_t)(i / GEMM_STAGES) & 1u;
+            const int s = i % STAGES;
+            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
             mbar_wait(smem_u32(&full_bar[s]), ph);
             tc_fence_after();
             if (lane == 0) {
@@ -148,26 +219,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
                     }
                 }
-                umma_commit(smem_u32(&empty_bar[s]));                      // stage reusable once these MMAs retire
+                umma_commit(smem_u32(&empty_bar[s]));                        // stage reusable once these MMAs retire
                 if (i == num_kb - 1) umma_commit(smem_u32(&tmem_full_bar));  // accumulator complete
             }
             __syncwarp();
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
+        // TMEM -> registers (thread = row) -> per-warp smem transpose -> coalesced global accesses
+        // (lane = column: every store/load/red instruction touches one contiguous 128-byte row segment).
         const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
-        const int row = m_tile * GEMM_BM + quarter * 32 + lane;
-        const bool row_ok = row < shape.M;
+        const int row0 = m_tile * GEMM_BM + quarter * 32;
         if (num_kb > 0) {
             mbar_wait(smem_u32(&tmem_full_bar), 0);
             tc_fence_after();
         }
-        float* out = ep.out_f32 ? ep.out_f32 + (long long)b1 * ep.out_b1 + (long long)b2 * ep.out_b2 + (long long)row * ep.ldo : nullptr;
-        const float* res = ep.resid ? ep.resid + (long long)b1 * ep.out_b1 + (long long)b2 * ep.out_b2 + (long long)row * ep.ldo : nullptr;
-        __nv_bfloat16* ohi = ep.out_hi ? ep.out_hi + (long long)b1 * ep.outs_b1 + (long long)b2 * ep.outs_b2 + (long long)row * ep.ldo_s : nullptr;
+        // All TMA loads have landed and all MMAs have retired: the pipeline stages are free to reuse.
+        float* stg = reinterpret_cast<float*>(smem_aligned) + (warp - 2) * (32 * 33);
+        const long long obase = (long long)b1 * ep.out_b1 + (long long)b2 * ep.out_b2;
+        float* out = ep.out_f32 ? ep.out_f32 + obase : nullptr;
+        const float* res = (ep.resid && !ep.accumulate) ? ep.resid + obase : nullptr;
+        __nv_bfloat16* ohi = ep.out_hi ? ep.out_hi + (long long)b1 * ep.outs_b1 + (long long)b2 * ep.outs_b2 : nullptr;
         const bool add_bias = ep.bias && split == 0;
+        const int nchunks = BN / 32;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < nchunks; ++c) {
+            const int col0 = n_tile * BN + c * 32;
+            if (col0 >= shape.N) break;
             uint32_t v[32];
             if (num_kb > 0) {
                 tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
@@ -176,67 +254,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                 for (int t = 0; t < 32; ++t) v[t] = 0u;
             }
-            const int col0 = n_tile * BN + c * 32;
-            if (!row_ok || col0 >= shape.N) continue;
-            const int ncols = min(32, shape.N - col0);
-            float f[32];
+            __syncwarp();
 #pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                float x = __uint_as_float(v[t]) * ep.alpha;
-                if (add_bias && t < ncols) x += ep.bias[col0 + t];
-                f[t] = x;
-            }
-            if (res && !ep.accumulate) {
-#pragma unroll
-                for (int t = 0; t < 32; ++t)
-                    if (t < ncols) f[t] += res[col0 + t];
-            }
-            if (ep.act != ACT_NONE) {
-#pragma unroll
-                for (int t = 0; t < 32; ++t) f[t] = apply_act(f[t], ep.act);
-            }
-            if (out) {
-                if (ep.accumulate) {
-#pragma unroll
-                    for (int t = 0; t < 32; ++t)
-                        if (t < ncols) atomicAdd(out + col0 + t, f[t]);
-                } else if (ncols == 32 && ((ep.ldo | col0) & 3) == 0) {
-#pragma unroll
-                    for (int t = 0; t < 32; t += 4)
-                        *reinterpret_cast<float4*>(out + col0 + t) = make_float4(f[t], f[t + 1], f[t + 2], f[t + 3]);
+            for (int t = 0; t < 32; ++t) stg[lane * 33 + t] = __uint_as_float(v[t]);
+            __syncwarp();
+            const int col = col0 + lane;
+            const bool col_ok = col < shape.N;
+            if (ohi == nullptr) {
+                const float bv = (add_bias && col_ok) ? ep.bias[col] : 0.f;
+#define PSAM_EPI_F32(A, R, C) epi_rows_f32<A, R, C>(stg, lane, row0, shape.M, col, col_ok, ep.alpha, bv, out, res, ep.ldo)
+                if (ep.accumulate) PSAM_EPI_F32(ACT_NONE, false, true);
+                else if (res) {
+                    if (ep.act == ACT_NONE) PSAM_EPI_F32(ACT_NONE, true, false);
+                    else if (ep.act == ACT_GELU) PSAM_EPI_F32(ACT_GELU, true, false);
+                    else PSAM_EPI_F32(ACT_RELU, true, false);
                 } else {
-#pragma unroll
-                    for (int t = 0; t < 32; ++t)
-                        if (t < ncols) out[col0 + t] = f[t];
+                    if (ep.act == ACT_NONE) PSAM_EPI_F32(ACT_NONE, false, false);
+                    else if (ep.act == ACT_GELU) PSAM_EPI_F32(ACT_GELU, false, false);
+                    else PSAM_EPI_F32(ACT_RELU, false, false);
                 }
-            }
-            if (ohi) {
-                __nv_bfloat16* olo = ohi + ep.out_plane;
-                if (ncols == 32 && ((ep.ldo_s | col0 | ep.out_plane) & 7) == 0) {
-#pragma unroll
-                    for (int t = 0; t < 32; t += 8) {
-                        uint32_t h[4], l[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            split_bf16(f[t + 2 * u], h0, l0);
-                            split_bf16(f[t + 2 * u + 1], h1, l1);
-                            h[u] = pack_bf16x2(h0, h1);
-                            l[u] = pack_bf16x2(l0, l1);
-                        }
-                        *reinterpret_cast<uint4*>(ohi + col0 + t) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4*>(olo + col0 + t) = make_uint4(l[0], l[1], l[2], l[3]);
-                    }
+#undef PSAM_EPI_F32
+            } else {
+                const float* bias = add_bias ? ep.bias : nullptr;
+                const bool va = ((ep.ldo_s | ep.out_plane | ep.outs_b1 | ep.outs_b2) & 1) == 0;
+#define PSAM_EPI_SP(A, R, F) epi_rows_split<A, R, F>(stg, lane, row0, shape.M, shape.N, col0, ep.alpha, bias, out, res, ep.ldo, ohi, ep.out_plane, ep.ldo_s, va)
+#define PSAM_EPI_SP_ACT(R, F)                                   \
+    if (ep.act == ACT_NONE) PSAM_EPI_SP(ACT_NONE, R, F);        \
+    else if (ep.act == ACT_GELU) PSAM_EPI_SP(ACT_GELU, R, F);   \
+    else PSAM_EPI_SP(ACT_RELU, R, F)
+                if (res) {
+                    if (out) { PSAM_EPI_SP_ACT(true, true); } else { PSAM_EPI_SP_ACT(true, false); }
                 } else {
-#pragma unroll
-                    for (int t = 0; t < 32; ++t)
-                        if (t < ncols) {
-                            __nv_bfloat16 h0, l0;
-                            split_bf16(f[t], h0, l0);
-                            ohi[col0 + t] = h0;
-                            olo[col0 + t] = l0;
-                        }
+                    if (out) { PSAM_EPI_SP_ACT(false, true); } else { PSAM_EPI_SP_ACT(false, false); }
                 }
+#undef PSAM_EPI_SP_ACT
+#undef PSAM_EPI_SP
             }
         }
     }
@@ -245,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, S::TMEM_COLS);
     }
 }
 
@@ -288,15 +340,35 @@ static int make_operand_map(CUtensorMap* map, const psam_operand* op, int box_ro
     return r == CUDA_SUCCESS ? PSAM_OK : (int)(1000 + r);
 }
 
-template <int BN>
+int make_operand_map_ext(CUtensorMap* map, const psam_operand* op, int box_rows) { return make_operand_map(map, op, box_rows); }
+
+template <int MAXBN, int STAGES>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& sh, const GemmEpilogue& ep,
                        cudaStream_t stream) {
-    auto kern = gemm_tc_kernel<BN>;
-    PSAM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
-    dim3 grid((unsigned)ceil_div(sh.N, BN), (unsigned)ceil_div(sh.M, GEMM_BM), (unsigned)(sh.nb1 * sh.nb2 * sh.split_k));
-    kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, stream>>>(ma, mb, sh, ep);
+    auto kern = gemm_tc_kernel<MAXBN, STAGES>;
+    using S = GemmSmem<MAXBN, STAGES>;
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    dim3 grid((unsigned)ceil_div(sh.N, sh.bn), (unsigned)ceil_div(sh.M, GEMM_BM), (unsigned)(sh.nb1 * sh.nb2 * sh.split_k));
+    kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ma, mb, sh, ep);
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
+}
+
+// Output-tile width: multiple of 32 in [32, 256] minimising (waves over 148 SMs) x (per-CTA cost), where the
+// per-CTA cost follows the operand bytes streamed per k-block (the kernel is L2->SM bandwidth bound).
+static int choose_bn(int M, int N, int K, int batches, int split_k) {
+    const int mt = ceil_div(M, GEMM_BM);
+    const int kb = ceil_div(ceil_div(K, GEMM_BK), split_k);
+    int best = 128;
+    double best_cost = 1e30;
+    for (int bn = (N >= 64 ? 64 : 32); bn <= 256; bn += 32) {
+        if (bn > 32 && bn - 32 >= N) break;
+        const long long tiles = (long long)ceil_div(N, bn) * mt * batches * split_k;
+        const long long waves = (tiles + 147) / 148;
+        const double cost = (double)waves * (6.0 * 256 + (double)kb * (128 + bn) + 0.35 * bn * 4);
+        if (cost < best_cost - 1e-9) best_cost = cost, best = bn;
+    }
+    return best;
 }
 
 }  // namespace psam
@@ -322,11 +394,19 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     ep.out_hi = (__nv_bfloat16*)o->out_hi, ep.out_plane = o->out_plane, ep.ldo_s = o->ldo_s;
     ep.outs_b1 = o->outs_b1, ep.outs_b2 = o->outs_b2;
     ep.bias = o->bias, ep.resid = o->resid, ep.alpha = o->alpha, ep.act = o->act, ep.accumulate = o->accumulate;
-    const int bn = (sh.N >= 128) ? 128 : 64;
+    int bn = choose_bn(sh.M, sh.N, sh.K, sh.nb1 * sh.nb2, sh.split_k);
+    if (const char* e = getenv("PSAM_GEMM_BN")) {  // tuning override (tools/gemm_bench.py)
+        const int v = atoi(e);
+        if (v >= 32 && v <= 256 && v % 32 == 0) bn = v;
+    }
+    sh.bn = bn;
     CUtensorMap ma, mb;
     int rc = make_operand_map(&ma, a, GEMM_BM);
     if (rc) return rc;
     rc = make_operand_map(&mb, w, bn);
     if (rc) return rc;
-    return bn == 128 ? launch_gemm<128>(ma, mb, sh, ep, stream) : launch_gemm<64>(ma, mb, sh, ep, stream);
+    if (bn <= 64) return launch_gemm<64, 4>(ma, mb, sh, ep, stream);
+    if (bn <= 128) return launch_gemm<128, 3>(ma, mb, sh, ep, stream);
+    if (bn <= 160) return launch_gemm<160, 3>(ma, mb, sh, ep, stream);
+    return launch_gemm<256, 2>(ma, mb, sh, ep, stream);
 }

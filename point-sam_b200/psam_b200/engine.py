@@ -8,6 +8,7 @@ lazily and cached per module; the cache is keyed on parameter storage/version so
 from __future__ import annotations
 
 import math
+from ctypes import byref
 from typing import Optional
 
 import torch
@@ -16,6 +17,7 @@ from . import native as nv
 from . import ops
 from .ops import ACT_GELU, ACT_NONE, ACT_RELU, Split
 
+FUSED_ATTENTION = True
 PASSES = 3  # split-bf16 (fp32-parity) mode; 1 = plain bf16 (fails the 1e-3 parity bound)
 
 
@@ -170,15 +172,8 @@ class _PackedEncoder:
         self.wout, self.bout = ops.pack_weight(enc.out_proj.weight), _f32(enc.out_proj.bias)
 
 
-def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
-    """x fp32 [B*L, D], updated in place (pre-LN residual block, rope=None)."""
-    dev = x.device
-    M = B * L
-    H, dh = pb.H, pb.dh
-    xn = Split(M, D, dev)
-    ops.layernorm(x, pb.g1, pb.b1, pb.eps1, out_split=xn)
-    qkv = Split(M, 3 * D, dev)
-    ops.gemm(xn, pb.wqkv, bias=pb.bqkv, out_split=qkv, passes=PASSES)
+def _attention_unfused(qkv: Split, att: Split, B: int, L: int, H: int, dh: int, D: int, dev):
+    """Fallback for head dims / sequence lengths the fused kernel does not cover (EVA-giant dh=88, L > 512)."""
     # V^T per (cloud, head): [B, H, dh, Lp]
     Lp = (L + 63) // 64 * 64
     vt = Split(B * H * dh, L, dev, pitch=Lp, zero=(Lp != L))
@@ -196,13 +191,32 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
     p = Split(B * H * L, L, dev, pitch=Lp, zero=(Lp != L))
     ops.softmax_split(s, L, dh ** -0.5, p)
     # O = P V  -> heads recombined into [M, D]
-    att = Split(M, D, dev)
     pa = p.operand(rows=L, k=L, nb1=H, b1_stride=L * Lp, nb2=B, b2_stride=H * L * Lp)
     va = vt.operand(rows=dh, k=L, nb1=H, b1_stride=dh * Lp, nb2=B, b2_stride=H * dh * Lp)
     o2 = ops.GemmOut()
     o2.out_hi, o2.out_plane, o2.ldo_s, o2.outs_b1, o2.outs_b2 = att.ptr(), att.plane, att.pitch, dh, L * att.pitch
     o2.alpha = 1.0
     ops.gemm_raw(pa, va, o2, PASSES, 1)
+
+
+def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
+    """x fp32 [B*L, D], updated in place (pre-LN residual block, rope=None)."""
+    dev = x.device
+    M = B * L
+    H, dh = pb.H, pb.dh
+    xn = Split(M, D, dev)
+    ops.layernorm(x, pb.g1, pb.b1, pb.eps1, out_split=xn)
+    qkv = Split(M, 3 * D, dev)
+    ops.gemm(xn, pb.wqkv, bias=pb.bqkv, out_split=qkv, passes=PASSES)
+    att = Split(M, D, dev)
+    if FUSED_ATTENTION and dh == 64 and L <= 512:
+        # fused tcgen05 attention: S stays in tensor memory, V^T is read as an MN-major operand
+        mk = lambda col: qkv.operand(rows=L, k=dh, col=col, nb1=H, b1_stride=dh, nb2=B, b2_stride=L * qkv.pitch)
+        qa, ka, va = mk(0), mk(D), mk(2 * D)
+        nv.check(nv.lib().psam_attention_bf16x3(byref(qa), byref(ka), byref(va), att.ptr(), att.plane, att.pitch, dh,
+                                               L * att.pitch, dh ** -0.5, nv.stream()), "attention_bf16x3")
+    else:
+        _attention_unfused(qkv, att, B, L, H, dh, D, dev)
     # x += proj(att)
     sk = _split_k_for(M, D, D)
     if sk > 1:

@@ -331,3 +331,27 @@ def test_linear_attention_posenc_misc():
     got = ops.add_bcast(a, bb, chunk=6 * 8, rep=2)
     want = a.reshape(4, 48) + bb.reshape(2, 48).repeat_interleave(2, 0)
     torch.testing.assert_close(got.reshape(4, 48), want, atol=0, rtol=0)
+
+
+@pytest.mark.parametrize("B,H,L", [(1, 16, 512), (2, 3, 128), (2, 2, 200), (1, 4, 333), (1, 2, 64)])
+def test_fused_attention_tc(B, H, L):
+    """psam_attention_bf16x3 (S in TMEM, exact softmax, MN-major V) vs fp64 softmax attention."""
+    from ctypes import byref
+
+    from psam_b200 import native as nv
+
+    ops = _ops()
+    dh = 64
+    D = H * dh
+    qkv = _rand(B * L, 3 * D, seed=21)
+    QKV = ops.Split(B * L, 3 * D, _dev())
+    ops.split_f32(qkv, QKV)
+    att = ops.Split(B * L, D, _dev())
+    mk = lambda col: QKV.operand(rows=L, k=dh, col=col, nb1=H, b1_stride=dh, nb2=B, b2_stride=L * QKV.pitch)
+    qa, ka, va = mk(0), mk(D), mk(2 * D)
+    nv.check(nv.lib().psam_attention_bf16x3(byref(qa), byref(ka), byref(va), att.ptr(), att.plane, att.pitch, dh,
+                                           L * att.pitch, dh ** -0.5, nv.stream()), "attention_bf16x3")
+    x = qkv.double().reshape(B, L, 3, H, dh).permute(2, 0, 3, 1, 4)
+    want = (torch.softmax(x[0] @ x[1].transpose(-1, -2) * dh ** -0.5, -1) @ x[2]).transpose(1, 2).reshape(B * L, D).float()
+    err = float((att.float() - want).abs().max())
+    assert err < 5e-5 * max(1.0, float(want.abs().max())), err
