@@ -12,8 +12,9 @@
 //   warp 1    MMA issuer: S_j = Q K_j^T (split-bf16, 3 passes) into TMEM columns [128j,128j+128);
 //             later O += P_j V_j with P from shared memory (K-major) and V^T taken directly from the
 //             row-major V block as an MN-major B operand (no transpose pass); O reuses columns [0,64)
-//   warps 2-5 softmax: thread = query row; tcgen05.ld S, row max, exp2, split P into bf16 hi/lo and
-//             write it 128B-swizzled into shared memory for the PV MMA; finally O / rowsum -> split-bf16
+//   warps 2-9 softmax: two threads per query row (each owns every other 32-key group); tcgen05.ld S, row
+//             max, ex2.approx, split P into bf16 hi/lo and write it 128B-swizzled into shared memory for
+//             the PV MMA; finally O / rowsum -> split-bf16
 // Numerics follow the split-bf16 scheme of gemm_tc.cu (x ~= hi + lo, three MMA passes).
 #include "psam_common.cuh"
 #include "../../include/psam_b200.h"
@@ -24,12 +25,12 @@ constexpr int ATT_BQ = 128;        // queries per CTA
 constexpr int ATT_BKEY = 128;      // keys per block
 constexpr int ATT_DH = 64;         // head dim handled by this kernel
 constexpr int ATT_STAGES = 3;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;  // TMA warp, MMA warp, 8 softmax warps (2 threads per query row)
 constexpr int ATT_TILE = 128 * 64 * 2;                 // one 128x64 bf16 tile (one plane)
 constexpr int ATT_SMEM_Q = 2 * ATT_TILE;               // hi + lo
 constexpr int ATT_SMEM_STAGE = 2 * ATT_TILE;           // hi + lo of a K or V block
 constexpr int ATT_SMEM_P = 2 * 2 * ATT_TILE;           // hi + lo, 2 k-blocks of 64 keys
-constexpr int ATT_SMEM_TOTAL = ATT_SMEM_Q + ATT_STAGES * ATT_SMEM_STAGE + ATT_SMEM_P + 1024;
+constexpr int ATT_SMEM_TOTAL = ATT_SMEM_Q + ATT_STAGES * ATT_SMEM_STAGE + ATT_SMEM_P + 1024 /*row exchange*/ + 1024 /*alignment*/;
 
 // MN-major (N contiguous), 128B-swizzled B operand: rows of the tile are K (keys), 64 N-elements = 128 B per
 // row, 8-row swizzle atoms 1024 B apart along K.
@@ -76,7 +77,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         tma_prefetch_desc(&tmap_v);
         mbar_init(smem_u32(&q_full), 1);
         mbar_init(smem_u32(&s_full), 1);
-        mbar_init(smem_u32(&p_full), 128);
+        mbar_init(smem_u32(&p_full), 256);
         mbar_init(smem_u32(&p_empty), 1);
         mbar_init(smem_u32(&o_full), 1);
         for (int s = 0; s < ATT_STAGES; ++s) {
@@ -171,48 +172,62 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             __syncwarp();
         }
     } else {
-        // ===================== softmax / epilogue warps (thread = query row) =====================
-        const int quarter = warp & 3;
-        const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
+        // ===================== softmax / epilogue warps (2 threads per query row) =====================
+        const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+        const int sub = (warp - 2) >> 2;          // 0/1: which half of the 32-column groups this thread owns
+        const int r = quarter * 32 + lane;        // row inside the tile == TMEM lane
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float* xchg = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn)) + ATT_SMEM_Q + ATT_STAGES * ATT_SMEM_STAGE +
+                                               ATT_SMEM_P);  // 2 x 128 floats, after the P buffer
         mbar_wait(smem_u32(&s_full), 0);
         tc_fence_after();
-        // ---- pass A: row maximum over all keys -------------------------------------------------
+        // ---- pass A: row maximum over all keys (each thread scans its half, halves combined through smem) ----
         float mx = -3.0e38f;
-        for (int j = 0; j < nkb; ++j) {
-#pragma unroll 1
-            for (int c = 0; c < ATT_BKEY / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_row + (uint32_t)(j * ATT_BKEY + c * 32), v);
-                tmem_ld_wait();
-                const int key0 = j * ATT_BKEY + c * 32;
+        for (int g = sub; g < nkb * (ATT_BKEY / 32); g += 2) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + (uint32_t)(g * 32), v);
+            tmem_ld_wait();
+            const int key0 = g * 32;
+            if (key0 + 32 <= p.L) {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(v[t]));
+            } else {
 #pragma unroll
                 for (int t = 0; t < 32; ++t)
                     if (key0 + t < p.L) mx = fmaxf(mx, __uint_as_float(v[t]));
             }
         }
+        xchg[sub * 128 + r] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 softmax warps only
+        mx = fmaxf(mx, xchg[(sub ^ 1) * 128 + r]);
         const float mscaled = mx * p.scale_log2e;
-        // ---- pass B: P_j = exp2(s*scale*log2e - m) -> shared memory, row sum -------------------------
+        // ---- pass B: P_j = exp2(s*scale*log2e - m) -> shared memory, partial row sum --------------------
         float lsum = 0.f;
         for (int j = 0; j < nkb; ++j) {
             if (j > 0) mbar_wait(smem_u32(&p_empty), (uint32_t)(j - 1) & 1u);  // PV_{j-1} has consumed P
 #pragma unroll 1
-            for (int c = 0; c < ATT_BKEY / 32; ++c) {
+            for (int c = sub; c < ATT_BKEY / 32; c += 2) {
                 uint32_t v[32];
                 tmem_ld_32x32(t_row + (uint32_t)(j * ATT_BKEY + c * 32), v);
                 tmem_ld_wait();
                 const int key0 = j * ATT_BKEY + c * 32;
+                const bool full = key0 + 32 <= p.L;
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int t = 0; t < 32; t += 2) {
-                    float e0 = (key0 + t < p.L) ? exp2f(fmaf(__uint_as_float(v[t]), p.scale_log2e, -mscaled)) : 0.f;
-                    float e1 = (key0 + t + 1 < p.L) ? exp2f(fmaf(__uint_as_float(v[t + 1]), p.scale_log2e, -mscaled)) : 0.f;
+                    float e0, e1;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(v[t]), p.scale_log2e, -mscaled)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(v[t + 1]), p.scale_log2e, -mscaled)));
+                    if (!full) {
+                        if (key0 + t >= p.L) e0 = 0.f;
+                        if (key0 + t + 1 >= p.L) e1 = 0.f;
+                    }
                     lsum += e0 + e1;
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(e0, h0, l0);
-                    split_bf16(e1, h1, l1);
-                    hi[t >> 1] = pack_bf16x2(h0, h1);
-                    lo[t >> 1] = pack_bf16x2(l0, l1);
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+                    const float2 hf = __bfloat1622float2(h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(e0 - hf.x, e1 - hf.y);
+                    hi[t >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                    lo[t >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
                 // keys [c*32, c*32+32) of this block: k-block kb = c/2, 16-byte chunks (c&1)*4 .. +3 of row r
                 const uint32_t rowbase = (uint32_t)((c >> 1) * ATT_TILE + r * 128);
@@ -227,15 +242,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             fence_proxy_async();    // generic-proxy smem writes -> visible to the async proxy (UMMA)
             mbar_arrive(smem_u32(&p_full));
         }
-        // ---- epilogue: O / rowsum -> split-bf16 [B*L, H*dh] --------------------------------------
+        // ---- epilogue: O / rowsum -> split-bf16 [B*L, H*dh]; thread `sub` stores 32 of the 64 columns ----
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // pass-A exchange values have been consumed by everyone
+        xchg[sub * 128 + r] = lsum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        lsum += xchg[(sub ^ 1) * 128 + r];
         mbar_wait(smem_u32(&o_full), 0);
         tc_fence_after();
         const int qrow = q_tile * ATT_BQ + r;
         const float inv = 1.0f / lsum;
         __nv_bfloat16* ohi = p.out_hi + (long long)b * p.out_b + (long long)h * p.out_h + (long long)qrow * p.ldo;
         __nv_bfloat16* olo = ohi + p.out_plane;
-#pragma unroll 1
-        for (int c = 0; c < ATT_DH / 32; ++c) {
+        {
+            const int c = sub;  // ATT_DH / 32 == 2 column groups
             uint32_t v[32];
             tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
             tmem_ld_wait();
