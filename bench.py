@@ -88,7 +88,10 @@ def cpu_reference_throughput(cfg, steps: int, warmup: int):
     from oracle import synth, torch_ref
 
     enc, N, G, K, bpg, P, kind = cfg
-    torch.set_num_threads(os.cpu_count() or 1)
+    # "all the host threads it can use": PyTorch's CPU GEMMs stop scaling (and regress badly) beyond a few dozen
+    # threads on many-socket hosts, so the thread count is capped; PSAM_CPU_THREADS overrides.
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(int(os.environ.get("PSAM_CPU_THREADS", min(ncpu, 32))))
     model = torch_ref.build_model(enc, G, K, seed=1234)
     clouds = [synth.make_batch(bpg, N, 0 + 17 * i, kind) for i in range(2)]
     prompts = [synth.make_prompts(c[0], P, i) for i, c in enumerate(clouds)]
@@ -283,6 +286,9 @@ def main():
             for i in range(3):
                 prof.records.clear()
                 pred._load(*devin[i % n_rot])
+                # keep the GPU busy (~25 ms) while the host enqueues the whole step, so that the event pairs
+                # bracket back-to-back kernels instead of host launch latency
+                torch.cuda._sleep(int(25e-3 * 1.9e9))
                 pred._run()
         stream.synchronize()
         nv._lib = real
@@ -297,8 +303,13 @@ def main():
         tot_ms = sum(s["ms"] for s in stages.values())
         achieved = g["flops"] / (g["ms"] / 1e3) / 1e12
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(REPO, "profiles", "r01_gemm_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 split-bf16)", "achieved": achieved, "peak": peak,
-                            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": f"{pk_src} sustained bf16",
+                            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": f"{pk_src} sustained bf16",
                             "executed_tflops": 3 * achieved, "executed_frac": 3 * achieved / peak,
                             "launches": g["n"], "avg_launch_us": g["ms"] / g["n"] * 1e3,
                             "share_of_step": g["ms"] / tot_ms,
