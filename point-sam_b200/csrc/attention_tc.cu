@@ -58,6 +58,7 @@ struct AttnParams {
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+    pdl_launch_dependents();
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t q_full, s_full, p_full, p_empty, o_full;
     __shared__ __align__(8) uint64_t kv_full[ATT_STAGES], kv_empty[ATT_STAGES];
@@ -91,6 +92,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();  // everything above is independent of the previous kernel; its outputs are read only below
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -313,7 +315,7 @@ extern "C" int psam_attention_bf16x3(const psam_operand* q, const psam_operand* 
     p.out_plane = out_plane, p.ldo = ldo, p.out_h = out_head_stride, p.out_b = out_cloud_stride;
     PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
     dim3 grid((unsigned)ceil_div(L, ATT_BQ), (unsigned)H, (unsigned)B);
-    attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, stream>>>(mq, mk, mv, p);
+    PSAM_CUDA_TRY(psam::launch(attention_tc_kernel, dim3(grid), dim3(ATT_THREADS), (size_t)(ATT_SMEM_TOTAL), stream, mq, mk, mv, p));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }

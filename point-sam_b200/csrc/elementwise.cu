@@ -54,6 +54,7 @@ __device__ __forceinline__ void ln_store(const psam_ln_args& a, long long row, i
 
 template <int VPL>  // values per lane, D <= 32*VPL
 __global__ void __launch_bounds__(256) layernorm_warp_kernel(const psam_ln_args a) {
+    pdl_prologue();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= a.rows) return;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(256) layernorm_warp_kernel(const psam_ln_args 
 
 template <int VPT>  // values per thread, D <= 256*VPT
 __global__ void __launch_bounds__(256) layernorm_block_kernel(const psam_ln_args a) {
+    pdl_prologue();
     __shared__ float red[8];
     const long long row = blockIdx.x;
     const float* x = a.x + row * a.ldx;
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(256)
 swiglu_ln_kernel(const float* __restrict__ gx, long long ld, long long x_off, int rows, int H, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ yh, long long y_plane, long long ldy_s,
                  long long pitch) {
+    pdl_prologue();
     __shared__ float red[8];
     const long long row = blockIdx.x;
     const float* g = gx + row * ld;
@@ -151,6 +154,7 @@ __global__ void small_in_linear_kernel(const float* __restrict__ x, int rows, in
                                        const float* __restrict__ b, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, float eps, int use_ln, int act,
                                        __nv_bfloat16* __restrict__ yh, long long y_plane, long long ldy_s) {
+    pdl_prologue();
     extern __shared__ float s_w[];  // [Cout*Cin] + [Cout] bias
     const int Cout = CPL * 32;
     for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) s_w[i] = W[i];
@@ -188,6 +192,7 @@ __global__ void small_in_linear_kernel(const float* __restrict__ x, int rows, in
 
 __global__ void group_max_kernel(const float* __restrict__ x, long long ldx, int groups, int K, int D, float* __restrict__ y,
                                  long long ldy, __nv_bfloat16* __restrict__ yh, long long y_plane, long long ldy_s) {
+    pdl_prologue();
     const int g = blockIdx.x;
     for (int c = threadIdx.x; c < D; c += blockDim.x) {
         const float* p = x + (long long)g * K * ldx + c;
@@ -200,6 +205,7 @@ __global__ void group_max_kernel(const float* __restrict__ x, long long ldx, int
 
 __global__ void softmax_split_kernel(const float* __restrict__ s, long long lds, long long rows, int L, float scale,
                                      __nv_bfloat16* __restrict__ ph, long long p_plane, long long ldp) {
+    pdl_prologue();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -217,6 +223,7 @@ __global__ void transpose_split_kernel(const __nv_bfloat16* __restrict__ src, lo
                                        long long src_z1, long long src_z2, __nv_bfloat16* __restrict__ dst,
                                        long long dst_plane, long long dst_ld, long long dst_z1, long long dst_z2, int rows,
                                        int cols, int nz1) {
+    pdl_prologue();
     __shared__ __nv_bfloat16 tile[2][32][34];
     const int z = blockIdx.z, z1 = z % nz1, z2 = z / nz1;
     src += z1 * src_z1 + z2 * src_z2;
@@ -242,6 +249,7 @@ __global__ void transpose_split_kernel(const __nv_bfloat16* __restrict__ src, lo
 __global__ void posenc_kernel(const float* __restrict__ coords, long long rows, const float* __restrict__ gauss, int F,
                               const int* __restrict__ labels, const float* __restrict__ emb0, const float* __restrict__ emb1,
                               float* __restrict__ out, int* __restrict__ bad_flag) {
+    pdl_prologue();
     const long long row = blockIdx.x;
     if (row >= rows) return;
     const float x = coords[row * 3], y = coords[row * 3 + 1], z = coords[row * 3 + 2];
@@ -278,6 +286,7 @@ template <int DH>
 __global__ void attention_small_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                                        float* __restrict__ o, int Z, int Lq, int Lk, int H, long long ldq, long long ldk,
                                        long long ldv, long long ldo) {
+    pdl_prologue();
     extern __shared__ float s_sc[];  // [warps][Lk] + [warps][DH] query
     const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long item = (long long)blockIdx.x * wpb + w;
@@ -326,6 +335,7 @@ __global__ void decoder_prepare_kernel(const float* __restrict__ iou_token, cons
                                        const float* __restrict__ sparse, int P, const float* __restrict__ pc_emb,
                                        const float* __restrict__ dense, long long dense_z, long long dense_g, int Z, int rep,
                                        int G, int D, float* __restrict__ tokens, float* __restrict__ src) {
+    pdl_prologue();
     const int T = 1 + nmt + P;
     const long long n_tok = (long long)Z * T * D, n_src = (long long)Z * G * D;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_tok + n_src; i += (long long)gridDim.x * blockDim.x) {
@@ -353,6 +363,7 @@ __global__ void interp_ln_gelu_kernel(const float* __restrict__ f, int Z, int re
                                       const float* __restrict__ w, int N, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ yh, long long y_plane,
                                       long long ldy_s) {
+    pdl_prologue();
     const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
     const long long total = (long long)Z * N;
     for (long long pt = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); pt < total; pt += (long long)gridDim.x * wpb) {
@@ -389,6 +400,7 @@ __global__ void interp_ln_gelu_kernel(const float* __restrict__ f, int Z, int re
 
 __global__ void mask_dot_kernel(const float* __restrict__ u, long long ldu, const float* __restrict__ hyper, int Z, int C, int N,
                                 int D, float* __restrict__ masks) {
+    pdl_prologue();
     extern __shared__ float s_h[];  // [C*D] for this z
     const int z = blockIdx.y;
     for (int i = threadIdx.x; i < C * D; i += blockDim.x) s_h[i] = hyper[(long long)z * C * D + i];
@@ -416,6 +428,7 @@ __global__ void mask_dot_kernel(const float* __restrict__ u, long long ldu, cons
 
 __global__ void add_bcast_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, long long chunk,
                                  long long rep, long long period, float* __restrict__ out) {
+    pdl_prologue();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const long long bi = ((i / chunk) / rep) * chunk + (i % chunk);
         out[i] = a[i] + b[bi % period];
@@ -424,6 +437,7 @@ __global__ void add_bcast_kernel(const float* __restrict__ a, const float* __res
 
 __global__ void split_f32_kernel(const float* __restrict__ x, long long ld, long long rows, int D, __nv_bfloat16* __restrict__ yh,
                                  long long y_plane, long long ldy_s, long long pitch) {
+    pdl_prologue();
     const long long total = rows * pitch;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / pitch;
@@ -434,6 +448,7 @@ __global__ void split_f32_kernel(const float* __restrict__ x, long long ld, long
 
 // fp32 SIMT linear: 64x64 tile, 256 threads, 4x4 per thread
 __global__ void __launch_bounds__(256) linear_f32_kernel(const psam_linear_args a) {
+    pdl_prologue();
     __shared__ float sx[16][65];
     __shared__ float sw[16][65];
     const int z = blockIdx.z;
@@ -493,6 +508,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const psam_linear_args 
 // fp32 SIMT linear for mid-size M (keys side of the decoder): 32x64 tile, BK=32, float4 loads along K,
 // all loads of a k-step in flight before the barrier.  Requires K%4==0, ldx%4==0, ldw%4==0.
 __global__ void __launch_bounds__(256) linear_f32_v4_kernel(const psam_linear_args a) {
+    pdl_prologue();
     __shared__ float sx[32][33];
     __shared__ float sw[32][65];
     const int z = blockIdx.z;
@@ -553,8 +569,9 @@ __global__ void __launch_bounds__(256) linear_f32_v4_kernel(const psam_linear_ar
 
 // Small-M fp32 linear (M <= 16): one warp per output column, lanes stride over K (coalesced weight
 // reads), all M rows accumulated at once.  The token side of the prompt decoder is all of this shape.
-template <int MR>
+template <int MR, bool VEC>
 __global__ void __launch_bounds__(256) linear_gemv_kernel(const psam_linear_args a) {
+    pdl_prologue();
     const int z = blockIdx.y;
     const float* x = a.x + z * a.x_z;
     const float* x2 = a.x2 ? a.x2 + z * a.x2_z : nullptr;
@@ -569,15 +586,32 @@ __global__ void __launch_bounds__(256) linear_gemv_kernel(const psam_linear_args
     float acc[MR];
 #pragma unroll
     for (int m = 0; m < MR; ++m) acc[m] = 0.f;
-    for (int k = lane; k < a.K; k += 32) {
-        const float wv = wr[k];
+    if (VEC) {
+#pragma unroll 2
+        for (int k = lane * 4; k < a.K; k += 128) {
+            const float4 wv = *reinterpret_cast<const float4*>(wr + k);
 #pragma unroll
-        for (int m = 0; m < MR; ++m)
-            if (m < a.M) {
-                float xv = x[(long long)m * a.ldx + k];
-                if (x2) xv += x2[(long long)m * a.ldx + k];
-                acc[m] = fmaf(xv, wv, acc[m]);
-            }
+            for (int m = 0; m < MR; ++m)
+                if (m < a.M) {
+                    float4 xv = *reinterpret_cast<const float4*>(x + (long long)m * a.ldx + k);
+                    if (x2) {
+                        const float4 t = *reinterpret_cast<const float4*>(x2 + (long long)m * a.ldx + k);
+                        xv.x += t.x, xv.y += t.y, xv.z += t.z, xv.w += t.w;
+                    }
+                    acc[m] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[m]))));
+                }
+        }
+    } else {
+        for (int k = lane; k < a.K; k += 32) {
+            const float wv = wr[k];
+#pragma unroll
+            for (int m = 0; m < MR; ++m)
+                if (m < a.M) {
+                    float xv = x[(long long)m * a.ldx + k];
+                    if (x2) xv += x2[(long long)m * a.ldx + k];
+                    acc[m] = fmaf(xv, wv, acc[m]);
+                }
+        }
     }
 #pragma unroll
     for (int m = 0; m < MR; ++m) {
@@ -610,18 +644,18 @@ extern "C" int psam_layernorm_f32(const psam_ln_args* a, cudaStream_t stream) {
     const bool block_per_row = (a->D > 1024) || (a->D >= 256 && a->rows <= 8192);
     if (block_per_row) {
         const int vpt = ceil_div(a->D, 256);
-        if (vpt <= 1) layernorm_block_kernel<1><<<a->rows, 256, 0, stream>>>(*a);
-        else if (vpt <= 2) layernorm_block_kernel<2><<<a->rows, 256, 0, stream>>>(*a);
-        else if (vpt <= 4) layernorm_block_kernel<4><<<a->rows, 256, 0, stream>>>(*a);
-        else if (vpt <= 8) layernorm_block_kernel<8><<<a->rows, 256, 0, stream>>>(*a);
-        else layernorm_block_kernel<16><<<a->rows, 256, 0, stream>>>(*a);
+        if (vpt <= 1) PSAM_CUDA_TRY(psam::launch(layernorm_block_kernel<1>, dim3(a->rows), dim3(256), (size_t)(0), stream, *a));
+        else if (vpt <= 2) PSAM_CUDA_TRY(psam::launch(layernorm_block_kernel<2>, dim3(a->rows), dim3(256), (size_t)(0), stream, *a));
+        else if (vpt <= 4) PSAM_CUDA_TRY(psam::launch(layernorm_block_kernel<4>, dim3(a->rows), dim3(256), (size_t)(0), stream, *a));
+        else if (vpt <= 8) PSAM_CUDA_TRY(psam::launch(layernorm_block_kernel<8>, dim3(a->rows), dim3(256), (size_t)(0), stream, *a));
+        else PSAM_CUDA_TRY(psam::launch(layernorm_block_kernel<16>, dim3(a->rows), dim3(256), (size_t)(0), stream, *a));
     } else {
         const int vpl = ceil_div(a->D, 32);
         const int blocks = ceil_div(a->rows, 8);
-        if (vpl <= 4) layernorm_warp_kernel<4><<<blocks, 256, 0, stream>>>(*a);
-        else if (vpl <= 8) layernorm_warp_kernel<8><<<blocks, 256, 0, stream>>>(*a);
-        else if (vpl <= 16) layernorm_warp_kernel<16><<<blocks, 256, 0, stream>>>(*a);
-        else layernorm_warp_kernel<32><<<blocks, 256, 0, stream>>>(*a);
+        if (vpl <= 4) PSAM_CUDA_TRY(psam::launch(layernorm_warp_kernel<4>, dim3(blocks), dim3(256), (size_t)(0), stream, *a));
+        else if (vpl <= 8) PSAM_CUDA_TRY(psam::launch(layernorm_warp_kernel<8>, dim3(blocks), dim3(256), (size_t)(0), stream, *a));
+        else if (vpl <= 16) PSAM_CUDA_TRY(psam::launch(layernorm_warp_kernel<16>, dim3(blocks), dim3(256), (size_t)(0), stream, *a));
+        else PSAM_CUDA_TRY(psam::launch(layernorm_warp_kernel<32>, dim3(blocks), dim3(256), (size_t)(0), stream, *a));
     }
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
@@ -634,7 +668,7 @@ extern "C" int psam_swiglu_ln(const float* gx, long long ld, long long x_off, in
     if (H > 8192) return PSAM_ERR_UNSUPPORTED;
     __nv_bfloat16* yh = (__nv_bfloat16*)y_hi;
     const int vpt = ceil_div(H, 256);
-#define PSAM_SWI(V) swiglu_ln_kernel<V><<<rows, 256, 0, stream>>>(gx, ld, x_off, rows, H, gamma, beta, eps, yh, y_plane, ldy_s, pitch)
+#define PSAM_SWI(V) PSAM_CUDA_TRY(psam::launch(swiglu_ln_kernel<V>, dim3(rows), dim3(256), (size_t)(0), stream, gx, ld, x_off, rows, H, gamma, beta, eps, yh, y_plane, ldy_s, pitch))
     if (vpt <= 2) PSAM_SWI(2);
     else if (vpt <= 4) PSAM_SWI(4);
     else if (vpt <= 8) PSAM_SWI(8);
@@ -656,8 +690,8 @@ extern "C" int psam_small_in_linear(const float* x, int rows, int Cin, const flo
     const int blocks = grid_for(rows, 8, 148 * 8);
     __nv_bfloat16* yh = (__nv_bfloat16*)y_hi;
 #define PSAM_SIL(CPL)                                                                                                     \
-    small_in_linear_kernel<CPL><<<blocks, 256, smem, stream>>>(x, rows, Cin, W, b, gamma, beta, eps, use_ln, act, yh, \
-                                                                 y_plane, ldy_s)
+    PSAM_CUDA_TRY(psam::launch(small_in_linear_kernel<CPL>, dim3(blocks), dim3(256), (size_t)(smem), stream, x, rows, Cin, W, b, gamma, beta, eps, use_ln, act, yh, \
+                                                                 y_plane, ldy_s))
     switch (Cout / 32) {
         case 1: PSAM_SIL(1); break;
         case 2: PSAM_SIL(2); break;
@@ -674,7 +708,7 @@ extern "C" int psam_small_in_linear(const float* x, int rows, int Cin, const flo
 extern "C" int psam_group_max(const float* x, long long ldx, int groups, int K, int D, float* y, long long ldy, void* y_hi,
                               long long y_plane, long long ldy_s, cudaStream_t stream) {
     if (!x || groups <= 0 || K <= 0 || D <= 0 || (!y && !y_hi)) return PSAM_ERR_ARG;
-    group_max_kernel<<<groups, 256, 0, stream>>>(x, ldx, groups, K, D, y, ldy, (__nv_bfloat16*)y_hi, y_plane, ldy_s);
+    PSAM_CUDA_TRY(psam::launch(group_max_kernel, dim3(groups), dim3(256), (size_t)(0), stream, x, ldx, groups, K, D, y, ldy, (__nv_bfloat16*)y_hi, y_plane, ldy_s));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -682,7 +716,7 @@ extern "C" int psam_group_max(const float* x, long long ldx, int groups, int K, 
 extern "C" int psam_softmax_split(const float* s, long long lds, long long rows, int L, float scale, void* p_hi,
                                   long long p_plane, long long ldp, cudaStream_t stream) {
     if (!s || !p_hi || rows <= 0 || L <= 0) return PSAM_ERR_ARG;
-    softmax_split_kernel<<<(unsigned)ceil_div_ll(rows, 8), 256, 0, stream>>>(s, lds, rows, L, scale, (__nv_bfloat16*)p_hi, p_plane, ldp);
+    PSAM_CUDA_TRY(psam::launch(softmax_split_kernel, dim3((unsigned)ceil_div_ll(rows, 8)), dim3(256), (size_t)(0), stream, s, lds, rows, L, scale, (__nv_bfloat16*)p_hi, p_plane, ldp));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -692,9 +726,9 @@ extern "C" int psam_transpose_split(const void* src_hi, long long src_plane, lon
                                     long long dst_z2, int rows, int cols, int nz1, int nz2, cudaStream_t stream) {
     if (!src_hi || !dst_hi || rows <= 0 || cols <= 0 || nz1 <= 0 || nz2 <= 0) return PSAM_ERR_ARG;
     dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32), nz1 * nz2);
-    transpose_split_kernel<<<grid, dim3(32, 8), 0, stream>>>((const __nv_bfloat16*)src_hi, src_plane, src_ld, src_z1, src_z2,
+    PSAM_CUDA_TRY(psam::launch(transpose_split_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), stream, (const __nv_bfloat16*)src_hi, src_plane, src_ld, src_z1, src_z2,
                                                              (__nv_bfloat16*)dst_hi, dst_plane, dst_ld, dst_z1, dst_z2, rows,
-                                                             cols, nz1);
+                                                             cols, nz1));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -703,7 +737,7 @@ extern "C" int psam_posenc_f32(const float* coords, long long rows, const float*
                                const float* emb0, const float* emb1, float* out, int* bad_flag, cudaStream_t stream) {
     if (!coords || !gauss || !out || rows <= 0 || F <= 0) return PSAM_ERR_ARG;
     if (labels && (!emb0 || !emb1)) return PSAM_ERR_ARG;
-    posenc_kernel<<<(unsigned)rows, 128, 0, stream>>>(coords, rows, gauss, F, labels, emb0, emb1, out, bad_flag);
+    PSAM_CUDA_TRY(psam::launch(posenc_kernel, dim3((unsigned)rows), dim3(128), (size_t)(0), stream, coords, rows, gauss, F, labels, emb0, emb1, out, bad_flag));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -719,7 +753,7 @@ extern "C" int psam_attention_f32(const float* q, const float* k, const float* v
 #define PSAM_ATT(DH)                                                                                                        \
     {                                                                                                                       \
         PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_small_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        attention_small_kernel<DH><<<grid, wpb * 32, smem, stream>>>(q, k, v, o, Z, Lq, Lk, H, ldq, ldk, ldv, ldo);         \
+        PSAM_CUDA_TRY(psam::launch(attention_small_kernel<DH>, dim3(grid), dim3(wpb * 32), (size_t)(smem), stream, q, k, v, o, Z, Lq, Lk, H, ldq, ldk, ldv, ldo));         \
     }
     if (dh == 16) PSAM_ATT(16)
     else if (dh == 32) PSAM_ATT(32)
@@ -736,8 +770,8 @@ extern "C" int psam_decoder_prepare(const float* iou_token, const float* mask_to
                                     int rep, int G, int D, float* tokens, float* src, cudaStream_t stream) {
     if (!iou_token || !mask_tokens || !pc_emb || !dense || !tokens || !src || Z <= 0 || rep <= 0 || (P > 0 && !sparse)) return PSAM_ERR_ARG;
     const long long total = (long long)Z * (1 + n_mask_tokens + P) * D + (long long)Z * G * D;
-    decoder_prepare_kernel<<<grid_for(total, 256), 256, 0, stream>>>(iou_token, mask_tokens, n_mask_tokens, sparse, P, pc_emb,
-                                                                     dense, dense_z, dense_g, Z, rep, G, D, tokens, src);
+    PSAM_CUDA_TRY(psam::launch(decoder_prepare_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), stream, iou_token, mask_tokens, n_mask_tokens, sparse, P, pc_emb,
+                                                                     dense, dense_z, dense_g, Z, rep, G, D, tokens, src));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -746,8 +780,8 @@ extern "C" int psam_interp_ln_gelu(const float* f, int Z, int rep, int G, int D,
                                    const float* gamma, const float* beta, float eps, void* y_hi, long long y_plane,
                                    long long ldy_s, cudaStream_t stream) {
     if (!f || !idx || !w || !gamma || !beta || !y_hi || Z <= 0 || rep <= 0 || D <= 0 || D > 1024) return PSAM_ERR_ARG;
-    interp_ln_gelu_kernel<<<grid_for((long long)Z * N, 8), 256, 0, stream>>>(f, Z, rep, G, D, idx, w, N, gamma, beta, eps,
-                                                                             (__nv_bfloat16*)y_hi, y_plane, ldy_s);
+    PSAM_CUDA_TRY(psam::launch(interp_ln_gelu_kernel, dim3(grid_for((long long)Z * N, 8)), dim3(256), (size_t)(0), stream, f, Z, rep, G, D, idx, w, N, gamma, beta, eps,
+                                                                             (__nv_bfloat16*)y_hi, y_plane, ldy_s));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -757,7 +791,7 @@ extern "C" int psam_mask_dot(const float* u, long long ldu, const float* hyper, 
     if (!u || !hyper || !masks || Z <= 0 || C <= 0 || C > 8 || N <= 0 || D <= 0) return PSAM_ERR_ARG;
     const size_t smem = (size_t)C * D * sizeof(float);
     dim3 grid(grid_for(N, 8, 148 * 8), Z);
-    mask_dot_kernel<<<grid, 256, smem, stream>>>(u, ldu, hyper, Z, C, N, D, masks);
+    PSAM_CUDA_TRY(psam::launch(mask_dot_kernel, dim3(grid), dim3(256), (size_t)(smem), stream, u, ldu, hyper, Z, C, N, D, masks));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -765,7 +799,7 @@ extern "C" int psam_mask_dot(const float* u, long long ldu, const float* hyper, 
 extern "C" int psam_add_bcast_f32(const float* a, const float* b, long long n, long long chunk, long long rep,
                                   long long b_period, float* out, cudaStream_t stream) {
     if (!a || !b || !out || n <= 0 || b_period <= 0 || chunk <= 0 || rep <= 0) return PSAM_ERR_ARG;
-    add_bcast_kernel<<<grid_for(n, 256), 256, 0, stream>>>(a, b, n, chunk, rep, b_period, out);
+    PSAM_CUDA_TRY(psam::launch(add_bcast_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), stream, a, b, n, chunk, rep, b_period, out));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -773,26 +807,31 @@ extern "C" int psam_add_bcast_f32(const float* a, const float* b, long long n, l
 extern "C" int psam_split_f32(const float* x, long long ld, long long rows, int D, void* y_hi, long long y_plane,
                               long long ldy_s, long long pitch, cudaStream_t stream) {
     if (!x || !y_hi || rows <= 0 || D <= 0 || pitch < D) return PSAM_ERR_ARG;
-    split_f32_kernel<<<grid_for(rows * pitch, 256), 256, 0, stream>>>(x, ld, rows, D, (__nv_bfloat16*)y_hi, y_plane, ldy_s, pitch);
+    PSAM_CUDA_TRY(psam::launch(split_f32_kernel, dim3(grid_for(rows * pitch, 256)), dim3(256), (size_t)(0), stream, x, ld, rows, D, (__nv_bfloat16*)y_hi, y_plane, ldy_s, pitch));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
 
 extern "C" int psam_linear_f32(const psam_linear_args* a, cudaStream_t stream) {
     if (!a || !a->x || !a->w || !a->y || a->M <= 0 || a->N <= 0 || a->K <= 0 || a->Z <= 0) return PSAM_ERR_ARG;
+    const bool vec_ok = a->K % 4 == 0 && a->ldx % 4 == 0 && a->ldw % 4 == 0 && ((uintptr_t)a->x % 16) == 0 && ((uintptr_t)a->w % 16) == 0 &&
+                        (!a->x2 || (uintptr_t)a->x2 % 16 == 0) && a->x_z % 4 == 0 && a->w_z % 4 == 0 && a->x2_z % 4 == 0;
     if (a->M <= 16) {
         dim3 grid(ceil_div(a->N, 8), a->Z);
-        if (a->M <= 1) linear_gemv_kernel<1><<<grid, 256, 0, stream>>>(*a);
-        else if (a->M <= 4) linear_gemv_kernel<4><<<grid, 256, 0, stream>>>(*a);
-        else if (a->M <= 8) linear_gemv_kernel<8><<<grid, 256, 0, stream>>>(*a);
-        else linear_gemv_kernel<16><<<grid, 256, 0, stream>>>(*a);
-    } else if (a->K % 4 == 0 && a->ldx % 4 == 0 && a->ldw % 4 == 0 && ((uintptr_t)a->x % 16) == 0 && ((uintptr_t)a->w % 16) == 0 &&
-               (!a->x2 || (uintptr_t)a->x2 % 16 == 0) && a->x_z % 4 == 0 && a->w_z % 4 == 0 && a->x2_z % 4 == 0) {
+#define PSAM_GEMV(MR)                                                                                              \
+    if (vec_ok) PSAM_CUDA_TRY(psam::launch(linear_gemv_kernel<MR, true>, grid, dim3(256), (size_t)0, stream, *a)); \
+    else PSAM_CUDA_TRY(psam::launch(linear_gemv_kernel<MR, false>, grid, dim3(256), (size_t)0, stream, *a))
+        if (a->M <= 1) { PSAM_GEMV(1); }
+        else if (a->M <= 4) { PSAM_GEMV(4); }
+        else if (a->M <= 8) { PSAM_GEMV(8); }
+        else { PSAM_GEMV(16); }
+#undef PSAM_GEMV
+    } else if (vec_ok) {
         dim3 grid(ceil_div(a->N, 64), ceil_div(a->M, 32), a->Z);
-        linear_f32_v4_kernel<<<grid, 256, 0, stream>>>(*a);
+        PSAM_CUDA_TRY(psam::launch(linear_f32_v4_kernel, dim3(grid), dim3(256), (size_t)(0), stream, *a));
     } else {
         dim3 grid(ceil_div(a->N, 64), ceil_div(a->M, 64), a->Z);
-        linear_f32_kernel<<<grid, 256, 0, stream>>>(*a);
+        PSAM_CUDA_TRY(psam::launch(linear_f32_kernel, dim3(grid), dim3(256), (size_t)(0), stream, *a));
     }
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;

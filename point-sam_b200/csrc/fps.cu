@@ -43,6 +43,7 @@ template <int PPT>
 __global__ void __launch_bounds__(FPS_THREADS, 1)
 fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long long* __restrict__ idx_out,
                    float* __restrict__ centers_out, float* __restrict__ ws) {
+    pdl_prologue();
     __shared__ __align__(16) uint4 slot_a[2][FPS_MAX_CLUSTER];  // records received from the cluster {bits, prio, x, y}
     __shared__ float slot_z[2][FPS_MAX_CLUSTER];
     __shared__ __align__(16) uint4 wrec_a[2][FPS_WARPS];        // per-warp records of this CTA
@@ -219,13 +220,15 @@ static int launch_fps(const float* xyz, int B, int N, int G, int log2T, long lon
     cfg.blockDim = dim3(FPS_THREADS);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     PSAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, N, G, log2T, idx, centers, ws));
     return PSAM_OK;
 }

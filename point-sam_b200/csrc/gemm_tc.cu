@@ -128,6 +128,7 @@ template <int MAXBN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmShape shape, const GemmEpilogue ep) {
+    pdl_launch_dependents();
     using S = GemmSmem<MAXBN, STAGES>;
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -167,6 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();  // everything above is independent of the previous kernel; its outputs are read only below
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -349,7 +351,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmS
     using S = GemmSmem<MAXBN, STAGES>;
     PSAM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     dim3 grid((unsigned)ceil_div(sh.N, sh.bn), (unsigned)ceil_div(sh.M, GEMM_BM), (unsigned)(sh.nb1 * sh.nb2 * sh.split_k));
-    kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(ma, mb, sh, ep);
+    PSAM_CUDA_TRY(psam::launch(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)(S::TOTAL), stream, ma, mb, sh, ep));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }

@@ -58,6 +58,7 @@ __device__ __forceinline__ void zero_counters(int* cnt) {
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_kernel(const float* __restrict__ query, const float* __restrict__ key, int Q, int N, int K, int sample_stride,
            int sample_cap, int cap, long long* __restrict__ idx_out, float* __restrict__ d2_out) {
+    pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_sample = reinterpret_cast<float*>(smem_raw);  // [sample_cap] (>= 2K); reused as the final list
     float* c_d2 = s_sample + sample_cap;                   // [cap]
@@ -229,6 +230,7 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ key, int Q
 __global__ void group_gather_kernel(const float* __restrict__ xyz, const float* __restrict__ feats,
                                     const float* __restrict__ centers, const long long* __restrict__ knn_idx, int B2,
                                     int rep, int N, int G, int K, int C, float inv_radius, float* __restrict__ out) {
+    pdl_prologue();
     const long long total = (long long)B2 * G * K;
     const int CO = 3 + C;
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
@@ -252,6 +254,7 @@ __global__ void group_gather_kernel(const float* __restrict__ xyz, const float* 
 __global__ void __launch_bounds__(256)
 knn3_interp_kernel(const float* __restrict__ xyz, const float* __restrict__ centers, int N, int G,
                    long long* __restrict__ idx_out, float* __restrict__ w_out) {
+    pdl_prologue();
     extern __shared__ float s_c[];  // [G*3]
     const int b = blockIdx.y;
     centers += (size_t)b * G * 3;
@@ -295,6 +298,7 @@ knn3_interp_kernel(const float* __restrict__ xyz, const float* __restrict__ cent
 __global__ void __launch_bounds__(256)
 nn_distance_kernel(const float* __restrict__ q, const float* __restrict__ key, int n1, int n2, float* __restrict__ dist,
                    long long* __restrict__ idx) {
+    pdl_prologue();
     __shared__ float s_k[256 * 3];
     const int i = blockIdx.x * 256 + threadIdx.x;
     float x = 0.f, y = 0.f, z = 0.f;
@@ -328,7 +332,7 @@ extern "C" int psam_nn_distance_f32(const float* query, const float* key, int n1
                                     long long* idx_out, cudaStream_t stream) {
     using namespace psam;
     if (!query || !key || !dist_out || n1 <= 0 || n2 <= 0) return PSAM_ERR_ARG;
-    nn_distance_kernel<<<ceil_div(n1, 256), 256, 0, stream>>>(query, key, n1, n2, dist_out, idx_out);
+    PSAM_CUDA_TRY(psam::launch(nn_distance_kernel, dim3(ceil_div(n1, 256)), dim3(256), (size_t)(0), stream, query, key, n1, n2, dist_out, idx_out));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -352,7 +356,7 @@ extern "C" int psam_knn_f32(const float* query, const float* key, int B, int Q, 
     if (cap < K) return PSAM_ERR_UNSUPPORTED;
     const size_t smem = (size_t)sample_cap * 4 + (size_t)cap * 8 + 64 * 4;
     PSAM_CUDA_TRY(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_kernel<<<dim3(Q, B), KNN_THREADS, smem, stream>>>(query, key, Q, N, K, stride, sample_cap, (int)cap, idx_out, d2_out);
+    PSAM_CUDA_TRY(psam::launch(knn_kernel, dim3(dim3(Q, B)), dim3(KNN_THREADS), (size_t)(smem), stream, query, key, Q, N, K, stride, sample_cap, (int)cap, idx_out, d2_out));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -364,8 +368,8 @@ extern "C" int psam_group_gather_f32(const float* xyz, const float* feats, const
     if (!xyz || !feats || !centers || !knn_idx || !groups_out || B <= 0 || rep <= 0 || C < 0) return PSAM_ERR_ARG;
     const long long total = (long long)B * rep * G * K;
     const int blocks = (int)min((long long)148 * 16, ceil_div_ll(total, 256));
-    group_gather_kernel<<<blocks, 256, 0, stream>>>(xyz, feats, centers, knn_idx, B * rep, rep, N, G, K, C,
-                                                    radius > 0.f ? 1.0f / radius : 1.0f, groups_out);
+    PSAM_CUDA_TRY(psam::launch(group_gather_kernel, dim3(blocks), dim3(256), (size_t)(0), stream, xyz, feats, centers, knn_idx, B * rep, rep, N, G, K, C,
+                                                    radius > 0.f ? 1.0f / radius : 1.0f, groups_out));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -377,7 +381,7 @@ extern "C" int psam_knn3_interp_f32(const float* xyz, const float* centers, int 
     const size_t smem = (size_t)G * 3 * sizeof(float);
     if (smem > 200 * 1024) return PSAM_ERR_UNSUPPORTED;
     PSAM_CUDA_TRY(cudaFuncSetAttribute(knn3_interp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn3_interp_kernel<<<dim3(ceil_div(N, 256), B), 256, smem, stream>>>(xyz, centers, N, G, idx_out, w_out);
+    PSAM_CUDA_TRY(psam::launch(knn3_interp_kernel, dim3(dim3(ceil_div(N, 256), B)), dim3(256), (size_t)(smem), stream, xyz, centers, N, G, idx_out, w_out));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }

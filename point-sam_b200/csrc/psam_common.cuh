@@ -6,6 +6,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <utility>
 
 #define PSAM_OK 0
 #define PSAM_ERR_ARG (-1)
@@ -24,6 +26,48 @@
     } while (0)
 
 namespace psam {
+
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every kernel of the path is launched with
+// programmaticStreamSerialization and starts with pdl_prologue() (griddepcontrol.launch_dependents +
+// griddepcontrol.wait).  The next kernel's CTAs are scheduled - and run their data-independent prologue
+// (barrier init, TMEM allocation, descriptor prefetch) - while this kernel drains; they block at
+// griddepcontrol.wait until this grid has completed and flushed.  Captured into the CUDA graph as
+// programmatic edges.  MEASURED on B200 (config c2, CUDA graph): 4.44 ms/step with PDL vs 4.18 ms without -
+// the early-scheduled dependents compete with the draining primary for SM resources - so it is OFF by default;
+// PSAM_PDL=1 enables it.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+    pdl_launch_dependents();
+    pdl_wait();
+}
+
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PSAM_PDL");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
