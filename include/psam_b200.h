@@ -88,6 +88,7 @@ typedef struct {
     float alpha;            /* accumulator scale (1.0f for a plain linear) */
     int act;                /* PSAM_ACT_* applied after bias/residual */
     int accumulate;         /* 1: out_f32 += alpha*acc (+bias) with red.add; required when split_k>1 */
+    int swiglu;             /* 1: W rows interleaved (gate_i, value_i); out_f32[:, i] = silu(gate_i)*value_i (fp32 out only) */
 } psam_gemm_out;
 
 /* C[M,N] = A[M,K] * W[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators).

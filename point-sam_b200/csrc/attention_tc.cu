@@ -99,8 +99,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         if (lane == 0) {
             const uint32_t qb = smem_u32(&q_full);
             mbar_arrive_expect_tx(qb, ATT_SMEM_Q);
-            tma_load_5d(sQ, &tmap_q, qb, 0, q_tile * ATT_BQ, 0, h, b);
-            tma_load_5d(sQ + ATT_TILE, &tmap_q, qb, 0, q_tile * ATT_BQ, 1, h, b);
+            tma_load_5d(sQ, &tmap_q, qb, 0, q_tile * ATT_BQ, 0, h, b);  // one 3-D box: hi plane then lo plane
             for (int i = 0; i < 2 * nkb; ++i) {  // K blocks then V blocks
                 const int s = i % ATT_STAGES;
                 const uint32_t ph = (uint32_t)(i / ATT_STAGES) & 1u;
@@ -110,7 +109,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                 const CUtensorMap* tm = (i < nkb) ? &tmap_k : &tmap_v;
                 const int j = (i < nkb) ? i : i - nkb;
                 tma_load_5d(sKV + s * ATT_SMEM_STAGE, tm, fb, 0, j * ATT_BKEY, 0, h, b);
-                tma_load_5d(sKV + s * ATT_SMEM_STAGE + ATT_TILE, tm, fb, 0, j * ATT_BKEY, 1, h, b);
             }
         }
     } else if (warp == 1) {
@@ -287,7 +285,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
 }
 
-int make_operand_map_ext(CUtensorMap* map, const psam_operand* op, int box_rows);  // gemm_tc.cu
+int make_operand_map_ext(CUtensorMap* map, const psam_operand* op, int box_rows, int box_planes);  // gemm_tc.cu
 
 }  // namespace psam
 
@@ -302,11 +300,11 @@ extern "C" int psam_attention_bf16x3(const psam_operand* q, const psam_operand* 
     if (k->rows != L || v->rows != L || k->k != dh || v->k != dh) return PSAM_ERR_ARG;
     if ((ldo | out_plane | out_head_stride | out_cloud_stride) & 7) return PSAM_ERR_ARG;
     CUtensorMap mq, mk, mv;
-    int rc = make_operand_map_ext(&mq, q, ATT_BQ);
+    int rc = make_operand_map_ext(&mq, q, ATT_BQ, 2);
     if (rc) return rc;
-    rc = make_operand_map_ext(&mk, k, ATT_BKEY);
+    rc = make_operand_map_ext(&mk, k, ATT_BKEY, 2);
     if (rc) return rc;
-    rc = make_operand_map_ext(&mv, v, ATT_BKEY);
+    rc = make_operand_map_ext(&mv, v, ATT_BKEY, 2);
     if (rc) return rc;
     AttnParams p;
     p.L = L, p.H = H, p.B = B;

@@ -115,6 +115,110 @@ __global__ void __launch_bounds__(256) layernorm_block_kernel(const psam_ln_args
         for (int c = a.D + threadIdx.x; c < a.pitch; c += 256) store_split((__nv_bfloat16*)a.y_hi, a.y_plane, row * a.ldy_s + c, 0.f);
 }
 
+
+// ---- float4-vectorised variants (D % 4 == 0, 16-byte aligned rows): 128-bit loads, 64-bit split stores ----
+__device__ __forceinline__ float4 ln_input4(const psam_ln_args& a, const float* x, const float* r, const float* gb, int c) {
+    float4 v = *reinterpret_cast<const float4*>(x + c);
+    if (r) {
+        const float4 t = *reinterpret_cast<const float4*>(r + c);
+        v.x += t.x, v.y += t.y, v.z += t.z, v.w += t.w;
+    }
+    if (gb) {
+        const float4 t = *reinterpret_cast<const float4*>(gb + c);
+        v.x += t.x, v.y += t.y, v.z += t.z, v.w += t.w;
+    }
+    return v;
+}
+
+__device__ __forceinline__ void ln_store4(const psam_ln_args& a, long long row, int c, float4 v, float mean, float rstd) {
+    const float4 g = *reinterpret_cast<const float4*>(a.gamma + c);
+    const float4 b = *reinterpret_cast<const float4*>(a.beta + c);
+    v.x = apply_act((v.x - mean) * rstd * g.x + b.x, a.act);
+    v.y = apply_act((v.y - mean) * rstd * g.y + b.y, a.act);
+    v.z = apply_act((v.z - mean) * rstd * g.z + b.z, a.act);
+    v.w = apply_act((v.w - mean) * rstd * g.w + b.w, a.act);
+    if (a.y) *reinterpret_cast<float4*>(a.y + row * a.ldy + c) = v;
+    if (a.y_hi) {
+        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(v.x, h0, l0);
+        split_bf16(v.y, h1, l1);
+        split_bf16(v.z, h2, l2);
+        split_bf16(v.w, h3, l3);
+        __nv_bfloat16* p = (__nv_bfloat16*)a.y_hi + row * a.ldy_s + c;
+        *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+        *reinterpret_cast<uint2*>(p + a.y_plane) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    }
+}
+
+template <int NV>  // float4 per lane, D <= 128*NV
+__global__ void __launch_bounds__(256) layernorm_warp_v4_kernel(const psam_ln_args a) {
+    pdl_prologue();
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= a.rows) return;
+    const float* x = a.x + row * a.ldx;
+    const float* r = a.r ? a.r + row * a.ldr : nullptr;
+    const float* gb = a.gbias ? a.gbias + (row / a.group_rows) * a.ld_gbias : nullptr;
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
+        v[i] = c < a.D ? ln_input4(a, x, r, gb, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / (float)a.D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (4 * lane + 128 * i < a.D) {
+            const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+            q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+    const float rstd = rsqrtf(warp_sum(q) / (float)a.D + a.eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = 4 * lane + 128 * i;
+        if (c < a.D) ln_store4(a, row, c, v[i], mean, rstd);
+    }
+    if (a.y_hi)
+        for (int c = a.D + lane; c < a.pitch; c += 32) store_split((__nv_bfloat16*)a.y_hi, a.y_plane, row * a.ldy_s + c, 0.f);
+}
+
+template <int NV>  // float4 per thread, D <= 1024*NV
+__global__ void __launch_bounds__(256) layernorm_block_v4_kernel(const psam_ln_args a) {
+    pdl_prologue();
+    __shared__ float red[8];
+    const long long row = blockIdx.x;
+    const float* x = a.x + row * a.ldx;
+    const float* r = a.r ? a.r + row * a.ldr : nullptr;
+    const float* gb = a.gbias ? a.gbias + (row / a.group_rows) * a.ld_gbias : nullptr;
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = 4 * threadIdx.x + 1024 * i;
+        v[i] = c < a.D ? ln_input4(a, x, r, gb, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = block_sum_256(s, red) / (float)a.D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (4 * threadIdx.x + 1024 * i < a.D) {
+            const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+            q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+    const float rstd = rsqrtf(block_sum_256(q, red) / (float)a.D + a.eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = 4 * threadIdx.x + 1024 * i;
+        if (c < a.D) ln_store4(a, row, c, v[i], mean, rstd);
+    }
+    if (a.y_hi)
+        for (int c = a.D + threadIdx.x; c < a.pitch; c += 256) store_split((__nv_bfloat16*)a.y_hi, a.y_plane, row * a.ldy_s + c, 0.f);
+}
+
 // SwiGLU + inner LayerNorm, one CTA per row, h = silu(g)*x computed once and kept in registers.
 template <int VPT>
 __global__ void __launch_bounds__(256)
@@ -358,11 +462,12 @@ __global__ void decoder_prepare_kernel(const float* __restrict__ iou_token, cons
     }
 }
 
-// one warp per point; D <= 1024 (D/32 values per lane)
-__global__ void interp_ln_gelu_kernel(const float* __restrict__ f, int Z, int rep, int G, int D, const long long* __restrict__ idx,
-                                      const float* __restrict__ w, int N, const float* __restrict__ gamma,
-                                      const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ yh, long long y_plane,
-                                      long long ldy_s) {
+// one warp per point; D % 128 == 0, D <= 1024: lane owns float4 columns 4*lane + 128*i (128-bit loads, 64-bit split stores)
+template <int NV>
+__global__ void __launch_bounds__(256)
+interp_ln_gelu_kernel(const float* __restrict__ f, int Z, int rep, int G, int D, const long long* __restrict__ idx,
+                      const float* __restrict__ w, int N, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                      __nv_bfloat16* __restrict__ yh, long long y_plane, long long ldy_s) {
     pdl_prologue();
     const int wpb = blockDim.x >> 5, lane = threadIdx.x & 31;
     const long long total = (long long)Z * N;
@@ -374,26 +479,39 @@ __global__ void interp_ln_gelu_kernel(const float* __restrict__ f, int Z, int re
         const float* f0 = f + ((long long)z * G + idx[o3]) * D;
         const float* f1 = f + ((long long)z * G + idx[o3 + 1]) * D;
         const float* f2 = f + ((long long)z * G + idx[o3 + 2]) * D;
-        float vals[32];
+        float4 v[NV];
         float s = 0.f;
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-            const int c = lane + 32 * t;
-            float v = 0.f;
-            if (c < D) v = (f0[c] * w0 + f1[c] * w1) + f2[c] * w2;
-            vals[t] = v;
-            s += v;
+        for (int i = 0; i < NV; ++i) {
+            const int c = 4 * lane + 128 * i;
+            const float4 a = *reinterpret_cast<const float4*>(f0 + c), b = *reinterpret_cast<const float4*>(f1 + c),
+                         d = *reinterpret_cast<const float4*>(f2 + c);
+            v[i].x = (a.x * w0 + b.x * w1) + d.x * w2;
+            v[i].y = (a.y * w0 + b.y * w1) + d.y * w2;
+            v[i].z = (a.z * w0 + b.z * w1) + d.z * w2;
+            v[i].w = (a.w * w0 + b.w * w1) + d.w * w2;
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
         const float mean = warp_sum(s) / (float)D;
         float q = 0.f;
 #pragma unroll
-        for (int t = 0; t < 32; ++t)
-            if (lane + 32 * t < D) q += (vals[t] - mean) * (vals[t] - mean);
+        for (int i = 0; i < NV; ++i) {
+            const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+            q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
         const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-            const int c = lane + 32 * t;
-            if (c < D) store_split(yh, y_plane, pt * ldy_s + c, gelu_erf((vals[t] - mean) * rstd * gamma[c] + beta[c]));
+        for (int i = 0; i < NV; ++i) {
+            const int c = 4 * lane + 128 * i;
+            const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+            __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+            split_bf16(gelu_erf((v[i].x - mean) * rstd * g.x + b.x), h0, l0);
+            split_bf16(gelu_erf((v[i].y - mean) * rstd * g.y + b.y), h1, l1);
+            split_bf16(gelu_erf((v[i].z - mean) * rstd * g.z + b.z), h2, l2);
+            split_bf16(gelu_erf((v[i].w - mean) * rstd * g.w + b.w), h3, l3);
+            __nv_bfloat16* p = yh + pt * ldy_s + c;
+            *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+            *reinterpret_cast<uint2*>(p + y_plane) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
         }
     }
 }
@@ -642,7 +760,24 @@ extern "C" int psam_layernorm_f32(const psam_ln_args* a, cudaStream_t stream) {
     if (a->gbias && a->group_rows <= 0) return PSAM_ERR_ARG;
     if (a->D > 4096) return PSAM_ERR_UNSUPPORTED;
     const bool block_per_row = (a->D > 1024) || (a->D >= 256 && a->rows <= 8192);
-    if (block_per_row) {
+    auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+    const bool vec = a->D % 4 == 0 && a->ldx % 4 == 0 && al(a->x) && al(a->gamma) && al(a->beta) &&
+                     (!a->r || (a->ldr % 4 == 0 && al(a->r))) && (!a->gbias || (a->ld_gbias % 4 == 0 && al(a->gbias))) &&
+                     (!a->y || (a->ldy % 4 == 0 && al(a->y))) &&
+                     (!a->y_hi || (a->ldy_s % 4 == 0 && a->y_plane % 4 == 0 && ((uintptr_t)a->y_hi & 7) == 0));
+    if (block_per_row && vec) {
+        const int nv = ceil_div(a->D, 1024);
+        if (nv <= 1) PSAM_CUDA_TRY(psam::launch(layernorm_block_v4_kernel<1>, dim3(a->rows), dim3(256), (size_t)0, stream, *a));
+        else if (nv <= 2) PSAM_CUDA_TRY(psam::launch(layernorm_block_v4_kernel<2>, dim3(a->rows), dim3(256), (size_t)0, stream, *a));
+        else PSAM_CUDA_TRY(psam::launch(layernorm_block_v4_kernel<4>, dim3(a->rows), dim3(256), (size_t)0, stream, *a));
+    } else if (!block_per_row && vec) {
+        const int nv = ceil_div(a->D, 128);
+        const int blocks = ceil_div(a->rows, 8);
+        if (nv <= 1) PSAM_CUDA_TRY(psam::launch(layernorm_warp_v4_kernel<1>, dim3(blocks), dim3(256), (size_t)0, stream, *a));
+        else if (nv <= 2) PSAM_CUDA_TRY(psam::launch(layernorm_warp_v4_kernel<2>, dim3(blocks), dim3(256), (size_t)0, stream, *a));
+        else if (nv <= 4) PSAM_CUDA_TRY(psam::launch(layernorm_warp_v4_kernel<4>, dim3(blocks), dim3(256), (size_t)0, stream, *a));
+        else PSAM_CUDA_TRY(psam::launch(layernorm_warp_v4_kernel<8>, dim3(blocks), dim3(256), (size_t)0, stream, *a));
+    } else if (block_per_row) {
         const int vpt = ceil_div(a->D, 256);
         if (vpt <= 1) PSAM_CUDA_TRY(psam::launch(layernorm_block_kernel<1>, dim3(a->rows), dim3(256), (size_t)(0), stream, *a));
         else if (vpt <= 2) PSAM_CUDA_TRY(psam::launch(layernorm_block_kernel<2>, dim3(a->rows), dim3(256), (size_t)(0), stream, *a));
@@ -779,9 +914,19 @@ extern "C" int psam_decoder_prepare(const float* iou_token, const float* mask_to
 extern "C" int psam_interp_ln_gelu(const float* f, int Z, int rep, int G, int D, const long long* idx, const float* w, int N,
                                    const float* gamma, const float* beta, float eps, void* y_hi, long long y_plane,
                                    long long ldy_s, cudaStream_t stream) {
-    if (!f || !idx || !w || !gamma || !beta || !y_hi || Z <= 0 || rep <= 0 || D <= 0 || D > 1024) return PSAM_ERR_ARG;
-    PSAM_CUDA_TRY(psam::launch(interp_ln_gelu_kernel, dim3(grid_for((long long)Z * N, 8)), dim3(256), (size_t)(0), stream, f, Z, rep, G, D, idx, w, N, gamma, beta, eps,
-                                                                             (__nv_bfloat16*)y_hi, y_plane, ldy_s));
+    if (!f || !idx || !w || !gamma || !beta || !y_hi || Z <= 0 || rep <= 0 || D <= 0) return PSAM_ERR_ARG;
+    if (D % 128 || D > 1024 || (ldy_s & 3) || (y_plane & 3)) return PSAM_ERR_UNSUPPORTED;
+    const dim3 grid(grid_for((long long)Z * N, 8)), block(256);
+    __nv_bfloat16* yh = (__nv_bfloat16*)y_hi;
+#define PSAM_INT(NV) PSAM_CUDA_TRY(psam::launch(interp_ln_gelu_kernel<NV>, grid, block, (size_t)0, stream, f, Z, rep, G, D, idx, w, N, gamma, beta, eps, yh, y_plane, ldy_s))
+    switch (D / 128) {
+        case 1: PSAM_INT(1); break;
+        case 2: PSAM_INT(2); break;
+        case 4: PSAM_INT(4); break;
+        case 8: PSAM_INT(8); break;
+        default: return PSAM_ERR_UNSUPPORTED;
+    }
+#undef PSAM_INT
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }

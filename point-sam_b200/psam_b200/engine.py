@@ -145,8 +145,9 @@ class _PackedBlock:
             Hp = (Hd + 63) // 64 * 64
             w1 = torch.zeros((2 * Hp, D), dtype=torch.float32, device=dev)
             b1 = torch.zeros(2 * Hp, dtype=torch.float32, device=dev)
-            w1[:Hd], w1[Hp:Hp + Hd] = mlp.fc1_g.weight.detach().float(), mlp.fc1_x.weight.detach().float()
-            b1[:Hd], b1[Hp:Hp + Hd] = mlp.fc1_g.bias.detach().float(), mlp.fc1_x.bias.detach().float()
+            # gate / value rows interleaved (2i, 2i+1): the GEMM epilogue computes silu(g) * x directly
+            w1[0:2 * Hd:2], w1[1:2 * Hd:2] = mlp.fc1_g.weight.detach().float(), mlp.fc1_x.weight.detach().float()
+            b1[0:2 * Hd:2], b1[1:2 * Hd:2] = mlp.fc1_g.bias.detach().float(), mlp.fc1_x.bias.detach().float()
             self.hid, self.hp = Hd, Hp
             self.w1, self.bb1 = ops.pack_weight(w1), b1
             self.gn, self.bn, self.epsn = _f32(mlp.norm.weight), _f32(mlp.norm.bias), mlp.norm.eps
@@ -226,10 +227,10 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
     # MLP
     ops.layernorm(x, pb.g2, pb.b2, pb.eps2, out_split=xn)
     if pb.swiglu:
-        gx = torch.empty((M, 2 * pb.hp), dtype=torch.float32, device=dev)
-        ops.gemm(xn, pb.w1, bias=pb.bb1, out_f32=gx, passes=PASSES)
-        h = Split(M, pb.hp, dev, pitch=pb.hp)  # columns hid..hp are zero-filled by swiglu_ln
-        ops.swiglu_ln(gx, pb.hid, pb.hp, pb.gn, pb.bn, pb.epsn, h)
+        hf = torch.empty((M, pb.hp), dtype=torch.float32, device=dev)
+        ops.gemm(xn, pb.w1, bias=pb.bb1, out_f32=hf, passes=PASSES, swiglu=True)  # hf = silu(fc1_g) * fc1_x
+        h = Split(M, pb.hp, dev, pitch=pb.hp)  # columns hid..hp are zero-filled by the LayerNorm kernel
+        ops.layernorm(hf, pb.gn, pb.bn, pb.epsn, D=pb.hid, out_split=h)
     else:
         h = Split(M, pb.hid, dev)
         ops.gemm(xn, pb.w1, bias=pb.bb1, out_split=h, act=ACT_GELU, passes=PASSES)

@@ -28,7 +28,8 @@ class GemmOut(Structure):
     _fields_ = [("out_f32", c_void_p), ("ldo", c_longlong), ("out_b1", c_longlong), ("out_b2", c_longlong),
                 ("out_hi", c_void_p), ("out_plane", c_longlong), ("ldo_s", c_longlong),
                 ("outs_b1", c_longlong), ("outs_b2", c_longlong),
-                ("bias", c_void_p), ("resid", c_void_p), ("alpha", c_float), ("act", c_int), ("accumulate", c_int)]
+                ("bias", c_void_p), ("resid", c_void_p), ("alpha", c_float), ("act", c_int), ("accumulate", c_int),
+                ("swiglu", c_int)]
 
 
 class LinearArgs(Structure):
