@@ -136,6 +136,7 @@ typedef struct {
     int rows, D, act;
     float* y; long long ldy;                  /* optional */
     void* y_hi; long long y_plane, ldy_s, pitch; /* optional split output */
+    int padded;                               /* 1: x rows (zeros), gamma, beta and outputs are valid up to roundup4(D) */
 } psam_ln_args;
 int psam_layernorm_f32(const psam_ln_args* args, cudaStream_t stream);
 

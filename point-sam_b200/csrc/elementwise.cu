@@ -172,7 +172,9 @@ __global__ void __launch_bounds__(256) layernorm_warp_v4_kernel(const psam_ln_ar
 #pragma unroll
     for (int i = 0; i < NV; ++i)
         if (4 * lane + 128 * i < a.D) {
-            const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+            const int c = 4 * lane + 128 * i;
+            const float d0 = v[i].x - mean, d1 = c + 1 < a.D ? v[i].y - mean : 0.f, d2 = c + 2 < a.D ? v[i].z - mean : 0.f,
+                        d3 = c + 3 < a.D ? v[i].w - mean : 0.f;
             q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
         }
     const float rstd = rsqrtf(warp_sum(q) / (float)a.D + a.eps);
@@ -206,7 +208,9 @@ __global__ void __launch_bounds__(256) layernorm_block_v4_kernel(const psam_ln_a
 #pragma unroll
     for (int i = 0; i < NV; ++i)
         if (4 * threadIdx.x + 1024 * i < a.D) {
-            const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+            const int c = 4 * threadIdx.x + 1024 * i;
+            const float d0 = v[i].x - mean, d1 = c + 1 < a.D ? v[i].y - mean : 0.f, d2 = c + 2 < a.D ? v[i].z - mean : 0.f,
+                        d3 = c + 3 < a.D ? v[i].w - mean : 0.f;
             q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
         }
     const float rstd = rsqrtf(block_sum_256(q, red) / (float)a.D + a.eps);
@@ -386,26 +390,31 @@ __global__ void posenc_kernel(const float* __restrict__ coords, long long rows, 
 // one warp per (z, head, query); scores kept in shared memory (Lk <= 4096).  Both phases split the KEYS across
 // lanes (the value phase accumulates dh partial sums per lane and reduces them with shuffles), so long
 // key sequences (tokens -> 512 patches) do not serialise on one lane.
-template <int DH>
+template <int DH, int WPI>  // WPI warps cooperate on one (z, head, query) item, each taking a slice of the keys
 __global__ void attention_small_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                                        float* __restrict__ o, int Z, int Lq, int Lk, int H, long long ldq, long long ldk,
                                        long long ldv, long long ldo) {
     pdl_prologue();
-    extern __shared__ float s_sc[];  // [warps][Lk] + [warps][DH] query
+    extern __shared__ float s_sc[];  // per warp: [Lk scores (only its slice used)] + [DH query] ; then WPI*(DH+2) combine area per item
     const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * wpb + w;
-    if (item >= (long long)Z * H * Lq) return;
-    const int i = (int)(item % Lq);
-    const int h = (int)((item / Lq) % H);
-    const int z = (int)(item / ((long long)Lq * H));
+    const int ipb = wpb / WPI;                 // items per block
+    const int sub = w % WPI;                   // key slice of this warp
+    const long long item = (long long)blockIdx.x * ipb + w / WPI;
+    const bool active = item < (long long)Z * H * Lq;
+    const int i = active ? (int)(item % Lq) : 0;
+    const int h = active ? (int)((item / Lq) % H) : 0;
+    const int z = active ? (int)(item / ((long long)Lq * H)) : 0;
     float* sc = s_sc + (size_t)w * (Lk + DH);
     float* sq = sc + Lk;
+    float* comb = s_sc + (size_t)wpb * (Lk + DH) + (size_t)(w / WPI) * WPI * (DH + 2);
     const float* qp = q + ((long long)z * Lq + i) * ldq + h * DH;
     for (int d = lane; d < DH; d += 32) sq[d] = qp[d];
     __syncwarp();
     const float scale = rsqrtf((float)DH);
+    const int kchunk = (Lk + WPI - 1) / WPI;
+    const int jbeg = sub * kchunk, jend = min(Lk, jbeg + kchunk);
     float m = -3.4e38f;
-    for (int j = lane; j < Lk; j += 32) {
+    for (int j = jbeg + lane; j < jend; j += 32) {
         const float* kp = k + ((long long)z * Lk + j) * ldk + h * DH;
         float acc = 0.f;
 #pragma unroll
@@ -419,19 +428,43 @@ __global__ void attention_small_kernel(const float* __restrict__ q, const float*
     float acc[DH];
 #pragma unroll
     for (int d = 0; d < DH; ++d) acc[d] = 0.f;
-    for (int j = lane; j < Lk; j += 32) {
+    for (int j = jbeg + lane; j < jend; j += 32) {
         const float e = __expf(sc[j] - m);
         sum += e;
         const float* vp = v + ((long long)z * Lk + j) * ldv + h * DH;
 #pragma unroll
         for (int d = 0; d < DH; ++d) acc[d] = fmaf(e, vp[d], acc[d]);
     }
-    const float inv = 1.0f / warp_sum(sum);
-    float* op = o + ((long long)z * Lq + i) * ldo + h * DH;
+    sum = warp_sum(sum);
 #pragma unroll
-    for (int d = 0; d < DH; ++d) {
-        const float t = warp_sum(acc[d]);
-        if (lane == (d & 31)) op[d] = t * inv;
+    for (int d = 0; d < DH; ++d) acc[d] = warp_sum(acc[d]);
+    float* op = o + ((long long)z * Lq + i) * ldo + h * DH;
+    if (WPI == 1) {
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int d = 0; d < DH; ++d)
+            if (active && lane == (d & 31)) op[d] = acc[d] * inv;
+    } else {
+        // combine the WPI partial (max, sum, acc) triples through shared memory
+        if (lane == 0) {
+            comb[sub * (DH + 2)] = m;
+            comb[sub * (DH + 2) + 1] = sum;
+        }
+#pragma unroll
+        for (int d = 0; d < DH; ++d)
+            if (lane == (d & 31)) comb[sub * (DH + 2) + 2 + d] = acc[d];
+        __syncthreads();
+        if (sub == 0 && active) {
+            float gm = -3.4e38f;
+            for (int t = 0; t < WPI; ++t) gm = fmaxf(gm, comb[t * (DH + 2)]);
+            float gs = 0.f;
+            for (int t = 0; t < WPI; ++t) gs += comb[t * (DH + 2) + 1] * __expf(comb[t * (DH + 2)] - gm);
+            for (int d = lane; d < DH; d += 32) {
+                float a2 = 0.f;
+                for (int t = 0; t < WPI; ++t) a2 += comb[t * (DH + 2) + 2 + d] * __expf(comb[t * (DH + 2)] - gm);
+                op[d] = a2 / gs;
+            }
+        }
     }
 }
 
@@ -744,6 +777,76 @@ __global__ void __launch_bounds__(256) linear_gemv_kernel(const psam_linear_args
     }
 }
 
+
+// Small-M fp32 linear, K split across the 8 warps of a CTA (each CTA owns 8 output columns): every lane issues
+// independent 128-bit loads over its K slice, partial sums meet in shared memory.  Used when K is long enough
+// that one-warp-per-column would serialise (token-side MLP lin2: K = 2048).  Requires K % 4 == 0, 16-byte rows.
+template <int MR>
+__global__ void __launch_bounds__(256) linear_gemv_ksplit_kernel(const psam_linear_args a) {
+    pdl_prologue();
+    __shared__ float part[8][8][MR];  // [warp][column][row]
+    const int z = blockIdx.y;
+    const float* x = a.x + z * a.x_z;
+    const float* x2 = a.x2 ? a.x2 + z * a.x2_z : nullptr;
+    const float* w = a.w + z * a.w_z;
+    const float* b = a.b ? a.b + z * a.b_z : nullptr;
+    const float* r = a.r ? a.r + z * a.r_z : nullptr;
+    float* y = a.y + z * a.y_z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n0 = blockIdx.x * 8;
+    const int kslice = ((a.K / 4 + 7) / 8) * 4;  // per-warp K range, multiple of 4
+    const int kbeg = warp * kslice, kend = min(a.K, kbeg + kslice);
+    float acc[8][MR];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int m = 0; m < MR; ++m) acc[c][m] = 0.f;
+    for (int k = kbeg + lane * 4; k < kend; k += 128) {
+        float4 xv[MR];
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            xv[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < a.M) {
+                xv[m] = *reinterpret_cast<const float4*>(x + (long long)m * a.ldx + k);
+                if (x2) {
+                    const float4 t = *reinterpret_cast<const float4*>(x2 + (long long)m * a.ldx + k);
+                    xv[m].x += t.x, xv[m].y += t.y, xv[m].z += t.z, xv[m].w += t.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (n0 + c < a.N) {
+                const float4 wv = *reinterpret_cast<const float4*>(w + (long long)(n0 + c) * a.ldw + k);
+#pragma unroll
+                for (int m = 0; m < MR; ++m)
+                    acc[c][m] = fmaf(xv[m].x, wv.x, fmaf(xv[m].y, wv.y, fmaf(xv[m].z, wv.z, fmaf(xv[m].w, wv.w, acc[c][m]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int m = 0; m < MR; ++m) {
+            const float t = warp_sum(acc[c][m]);
+            if (lane == 0) part[warp][c][m] = t;
+        }
+    __syncthreads();
+    if (threadIdx.x < 8 * MR) {
+        const int c = threadIdx.x / MR, m = threadIdx.x % MR;
+        const int n = n0 + c;
+        if (n < a.N && m < a.M) {
+            float v = 0.f;
+#pragma unroll
+            for (int wq = 0; wq < 8; ++wq) v += part[wq][c][m];
+            if (b) v += b[n];
+            v = apply_act(v, a.act);
+            if (r) v += r[(long long)m * a.ldy + n];
+            y[(long long)m * a.ldy + n] = v;
+        }
+    }
+}
+
 static inline int grid_for(long long work, int per_block, int max_blocks = 148 * 32) {
     long long g = (work + per_block - 1) / per_block;
     if (g < 1) g = 1;
@@ -761,7 +864,7 @@ extern "C" int psam_layernorm_f32(const psam_ln_args* a, cudaStream_t stream) {
     if (a->D > 4096) return PSAM_ERR_UNSUPPORTED;
     const bool block_per_row = (a->D > 1024) || (a->D >= 256 && a->rows <= 8192);
     auto al = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
-    const bool vec = a->D % 4 == 0 && a->ldx % 4 == 0 && al(a->x) && al(a->gamma) && al(a->beta) &&
+    const bool vec = (a->D % 4 == 0 || a->padded) && a->ldx % 4 == 0 && al(a->x) && al(a->gamma) && al(a->beta) &&
                      (!a->r || (a->ldr % 4 == 0 && al(a->r))) && (!a->gbias || (a->ld_gbias % 4 == 0 && al(a->gbias))) &&
                      (!a->y || (a->ldy % 4 == 0 && al(a->y))) &&
                      (!a->y_hi || (a->ldy_s % 4 == 0 && a->y_plane % 4 == 0 && ((uintptr_t)a->y_hi & 7) == 0));
@@ -881,14 +984,21 @@ extern "C" int psam_attention_f32(const float* q, const float* k, const float* v
                                   int dh, long long ldq, long long ldk, long long ldv, long long ldo, cudaStream_t stream) {
     if (!q || !k || !v || !o || Z <= 0 || Lq <= 0 || Lk <= 0 || H <= 0 || dh <= 0) return PSAM_ERR_ARG;
     const int wpb = 4;
-    const size_t smem = (size_t)wpb * (Lk + dh) * sizeof(float);
-    if (smem > 200 * 1024) return PSAM_ERR_UNSUPPORTED;
     const long long items = (long long)Z * H * Lq;
-    const unsigned grid = (unsigned)ceil_div_ll(items, wpb);
-#define PSAM_ATT(DH)                                                                                                        \
-    {                                                                                                                       \
-        PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_small_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        PSAM_CUDA_TRY(psam::launch(attention_small_kernel<DH>, dim3(grid), dim3(wpb * 32), (size_t)(smem), stream, q, k, v, o, Z, Lq, Lk, H, ldq, ldk, ldv, ldo));         \
+    const bool split = items <= 512 && Lk >= 128;  // few queries, many keys: 4 warps per item split the keys
+    const int wpi = split ? 4 : 1;
+    const size_t smem = (size_t)wpb * (Lk + dh) * sizeof(float) + (size_t)(wpb / wpi) * wpi * (dh + 2) * sizeof(float);
+    if (smem > 200 * 1024) return PSAM_ERR_UNSUPPORTED;
+    const unsigned grid = (unsigned)ceil_div_ll(items, wpb / wpi);
+#define PSAM_ATT(DH)                                                                                                              \
+    {                                                                                                                             \
+        if (split) {                                                                                                              \
+            PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_small_kernel<DH, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            PSAM_CUDA_TRY(psam::launch(attention_small_kernel<DH, 4>, dim3(grid), dim3(wpb * 32), smem, stream, q, k, v, o, Z, Lq, Lk, H, ldq, ldk, ldv, ldo)); \
+        } else {                                                                                                                  \
+            PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_small_kernel<DH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            PSAM_CUDA_TRY(psam::launch(attention_small_kernel<DH, 1>, dim3(grid), dim3(wpb * 32), smem, stream, q, k, v, o, Z, Lq, Lk, H, ldq, ldk, ldv, ldo)); \
+        }                                                                                                                         \
     }
     if (dh == 16) PSAM_ATT(16)
     else if (dh == 32) PSAM_ATT(32)
@@ -961,7 +1071,12 @@ extern "C" int psam_linear_f32(const psam_linear_args* a, cudaStream_t stream) {
     if (!a || !a->x || !a->w || !a->y || a->M <= 0 || a->N <= 0 || a->K <= 0 || a->Z <= 0) return PSAM_ERR_ARG;
     const bool vec_ok = a->K % 4 == 0 && a->ldx % 4 == 0 && a->ldw % 4 == 0 && ((uintptr_t)a->x % 16) == 0 && ((uintptr_t)a->w % 16) == 0 &&
                         (!a->x2 || (uintptr_t)a->x2 % 16 == 0) && a->x_z % 4 == 0 && a->w_z % 4 == 0 && a->x2_z % 4 == 0;
-    if (a->M <= 16) {
+    if (a->M <= 8 && vec_ok && a->K >= 512) {
+        dim3 grid(ceil_div(a->N, 8), a->Z);
+        if (a->M <= 1) PSAM_CUDA_TRY(psam::launch(linear_gemv_ksplit_kernel<1>, grid, dim3(256), (size_t)0, stream, *a));
+        else if (a->M <= 4) PSAM_CUDA_TRY(psam::launch(linear_gemv_ksplit_kernel<4>, grid, dim3(256), (size_t)0, stream, *a));
+        else PSAM_CUDA_TRY(psam::launch(linear_gemv_ksplit_kernel<8>, grid, dim3(256), (size_t)0, stream, *a));
+    } else if (a->M <= 16) {
         dim3 grid(ceil_div(a->N, 8), a->Z);
 #define PSAM_GEMV(MR)                                                                                              \
     if (vec_ok) PSAM_CUDA_TRY(psam::launch(linear_gemv_kernel<MR, true>, grid, dim3(256), (size_t)0, stream, *a)); \

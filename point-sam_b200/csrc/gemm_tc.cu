@@ -30,7 +30,8 @@ namespace psam {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+constexpr int GEMM_EPI_PER_QUARTER = 4;
+constexpr int GEMM_THREADS = 64 + 128 * GEMM_EPI_PER_QUARTER;  // TMA warp, MMA warp, 16 epilogue warps (four per TMEM lane quarter)
 
 struct GemmEpilogue {
     float* out_f32;            // may be null
@@ -256,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         // All TMA loads have landed and all MMAs have retired: the pipeline stages are free to reuse.
         float* stg = reinterpret_cast<float*>(smem_aligned) + (warp - 2) * (32 * 33);
-        const int ehalf = (warp - 2) >> 2;  // the two warps of a lane quarter take alternate 32-column chunks
+        const int ehalf = (warp - 2) >> 2;  // the warps of a lane quarter take interleaved 32-column chunks
         const long long obase = (long long)b1 * ep.out_b1 + (long long)b2 * ep.out_b2;
         float* out = ep.out_f32 ? ep.out_f32 + obase : nullptr;
         const float* res = (ep.resid && !ep.accumulate) ? ep.resid + obase : nullptr;
@@ -264,7 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool add_bias = ep.bias && split == 0;
         const int nchunks = BN / 32;
 #pragma unroll 1
-        for (int c = ehalf; c < nchunks; c += 2) {
+        for (int c = ehalf; c < nchunks; c += GEMM_EPI_PER_QUARTER) {
             const int col0 = n_tile * BN + c * 32;
             if (col0 >= shape.N) break;
             uint32_t v[32];

@@ -150,7 +150,10 @@ class _PackedBlock:
             b1[0:2 * Hd:2], b1[1:2 * Hd:2] = mlp.fc1_g.bias.detach().float(), mlp.fc1_x.bias.detach().float()
             self.hid, self.hp = Hd, Hp
             self.w1, self.bb1 = ops.pack_weight(w1), b1
-            self.gn, self.bn, self.epsn = _f32(mlp.norm.weight), _f32(mlp.norm.bias), mlp.norm.eps
+            gpad = torch.zeros(Hp, dtype=torch.float32, device=dev)
+            bpad = torch.zeros(Hp, dtype=torch.float32, device=dev)
+            gpad[:Hd], bpad[:Hd] = mlp.norm.weight.detach().float(), mlp.norm.bias.detach().float()
+            self.gn, self.bn, self.epsn = gpad, bpad, mlp.norm.eps  # zero-padded to Hp for the float4 LN path
             w2 = torch.zeros((D, Hp), dtype=torch.float32, device=dev)
             w2[:, :Hd] = mlp.fc2.weight.detach().float()
             self.w2, self.bb2 = ops.pack_weight(w2), _f32(mlp.fc2.bias)
@@ -230,7 +233,7 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
         hf = torch.empty((M, pb.hp), dtype=torch.float32, device=dev)
         ops.gemm(xn, pb.w1, bias=pb.bb1, out_f32=hf, passes=PASSES, swiglu=True)  # hf = silu(fc1_g) * fc1_x
         h = Split(M, pb.hp, dev, pitch=pb.hp)  # columns hid..hp are zero-filled by the LayerNorm kernel
-        ops.layernorm(hf, pb.gn, pb.bn, pb.epsn, D=pb.hid, out_split=h)
+        ops.layernorm(hf, pb.gn, pb.bn, pb.epsn, D=pb.hid, out_split=h, padded=True)
     else:
         h = Split(M, pb.hid, dev)
         ops.gemm(xn, pb.w1, bias=pb.bb1, out_split=h, act=ACT_GELU, passes=PASSES)

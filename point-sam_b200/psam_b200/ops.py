@@ -154,7 +154,7 @@ def linear_f32(x, w, b=None, *, x2=None, r=None, act=ACT_NONE, out=None, M=None,
 
 
 def layernorm(x, gamma, beta, eps, *, rows=None, D=None, r=None, gbias=None, group_rows=0, act=ACT_NONE,
-              out_f32: Optional[torch.Tensor] = None, out_split: Optional[Split] = None, ldx=None):
+              out_f32: Optional[torch.Tensor] = None, out_split: Optional[Split] = None, ldx=None, padded: bool = False):
     D = D if D is not None else x.shape[-1]
     rows = rows if rows is not None else x.numel() // x.shape[-1]
     a = LnArgs()
@@ -166,6 +166,7 @@ def layernorm(x, gamma, beta, eps, *, rows=None, D=None, r=None, gbias=None, gro
     a.y, a.ldy = nv.ptr(out_f32), (out_f32.shape[-1] if out_f32 is not None else 0)
     if out_split is not None:
         a.y_hi, a.y_plane, a.ldy_s, a.pitch = out_split.ptr(), out_split.plane, out_split.pitch, out_split.pitch
+    a.padded = int(padded)
     nv.check(nv.lib().psam_layernorm_f32(byref(a), nv.stream()), "layernorm")
 
 
