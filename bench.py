@@ -4,7 +4,10 @@
   python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--config c2] [--no-graph]
 
 A "step" = one pass of the hot path (FPS + kNN grouping + mini-PointNet + ViT-L encoder + prompt decoder ->
-mask logits) over one batch of synthetic clouds per GPU.  `value` times it with inputs resident in HBM;
+mask logits) over one batch of synthetic clouds per GPU (config c2: ONE cloud per step).  Steps are independent
+clouds, so up to `--depth` of them are in flight per GPU on separate streams / CUDA graphs (PipelinedPredictor):
+throughput is clouds completed per second; the single-stream latency of one cloud is reported in `config`.
+`value` times it with inputs resident in HBM;
 `e2e` times the same call through the public predictor API with HOST (pinned) buffers, H2D of the cloud
 and prompts and D2H of logits+IoU inside the timed region.  Multi-GPU: one process per GPU (torchrun),
 clouds sharded by rank, weights replicated, one NCCL all_gather of the per-rank metric at the end.
@@ -170,6 +173,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="c2")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--depth", type=int, default=8, help="clouds in flight per GPU (independent streams/graphs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -202,9 +206,12 @@ def main():
     host = [tuple(t.pin_memory() for t in (c[0], c[1], p[0], p[1])) for c, p in zip(clouds, prompts)]
     devin = [tuple(t.to(dev) for t in h) for h in host]
 
-    pred = model.make_predictor(bpg, N, P, True, use_graph=not args.no_graph)
-    pred.warmup(*devin[0])
+    pp = model.make_pipelined_predictor(bpg, N, P, depth=max(1, args.depth), use_graph=not args.no_graph)
+    pp.warmup(*devin[0])
+    pp.enable_host_results(3)
+    pred = pp.lanes[0]
     stream = pred.stream
+    main = torch.cuda.current_stream()
 
     def barrier():
         torch.cuda.synchronize()
@@ -213,14 +220,19 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """Device-side time of `steps` submissions: e0 on the main stream gates every lane, e1 follows all lanes."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        with torch.cuda.stream(stream):
-            e0.record()
+        e0.record(main)
+        for lane in pp.lanes:
+            lane.stream.wait_event(e0)
         for i in range(steps):
             fn(i)
-        with torch.cuda.stream(stream):
-            e1.record()
+        for lane in pp.lanes:
+            done = torch.cuda.Event()
+            done.record(lane.stream)
+            main.wait_event(done)
+        e1.record(main)
         barrier()
         ms = e0.elapsed_time(e1)
         if dist is not None:
@@ -231,7 +243,7 @@ def main():
 
     # ---- arm 1: inputs resident in HBM ---------------------------------------------------------
     def step_dev(i):
-        pred(*devin[i % n_rot])
+        pp.submit(*devin[i % n_rot])
 
     timed(step_dev, args.warmup)
     sampler = ClockSampler(local)
@@ -240,20 +252,20 @@ def main():
     ms_dev = timed(step_dev, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- arm 2: end to end with host buffers (H2D inputs, D2H logits + IoU) ----------------------
-    C = 3
-    out_m = torch.empty((bpg, C, N), dtype=torch.float32).pin_memory()
-    out_i = torch.empty((bpg, C), dtype=torch.float32).pin_memory()
+    # single-stream latency of one cloud (no overlap between clouds), for the record
+    def step_single(i):
+        pred(*devin[i % n_rot])
 
+    ms_single = timed(step_single, max(3, args.steps // 3)) / max(3, args.steps // 3)
+
+    # ---- arm 2: end to end with host buffers (H2D inputs, D2H logits + IoU, every result read) ----
     def step_e2e(i):
-        m, s = pred(*host[i % n_rot])
-        with torch.cuda.stream(stream):
-            out_m.copy_(m, non_blocking=True)
-            out_i.copy_(s, non_blocking=True)
-        stream.synchronize()  # the caller reads the result of every step
+        pp.wait_lane_free(pp.count)  # the host has consumed the previous result of this lane
+        pp.submit(*host[i % n_rot], to_host=True)
 
     timed(step_e2e, args.warmup)
     ms_e2e = timed(step_e2e, args.steps)
+    out_m, out_i = pp.host_out[0]
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     d2h = out_m.numel() * 4 + out_i.numel() * 4
 
@@ -270,7 +282,9 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3", "data": "synthetic", "config": workload_config(args, cfg, pred.graph is not None),
+            "dtype": "bf16x3", "data": "synthetic", "config": dict(workload_config(args, cfg, pred.graph is not None),
+                                                                    clouds_in_flight=pp.depth,
+                                                                    single_stream_ms_per_cloud=ms_single),
             "e2e": {"value": e2e, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": pred.launches_per_step * args.steps, "launches_per_step": pred.launches_per_step,

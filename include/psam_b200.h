@@ -89,6 +89,7 @@ typedef struct {
     int act;                /* PSAM_ACT_* applied after bias/residual */
     int accumulate;         /* 1: out_f32 += alpha*acc (+bias) with red.add; required when split_k>1 */
     int swiglu;             /* 1: W rows interleaved (gate_i, value_i); out_f32[:, i] = silu(gate_i)*value_i (fp32 out only) */
+    int tile_hint;          /* 0: tile width for lowest latency; 1: for lowest SM-time (several clouds in flight); 32..256: explicit */
 } psam_gemm_out;
 
 /* C[M,N] = A[M,K] * W[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators).

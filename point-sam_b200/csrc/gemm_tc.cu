@@ -381,7 +381,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmS
 
 // Output-tile width: multiple of 32 in [32, 256] minimising (waves over 148 SMs) x (per-CTA cost), where the
 // per-CTA cost follows the operand bytes streamed per k-block (the kernel is L2->SM bandwidth bound).
-static int choose_bn(int M, int N, int K, int batches, int split_k) {
+static int choose_bn(int M, int N, int K, int batches, int split_k, bool throughput) {
     const int mt = ceil_div(M, GEMM_BM);
     const int kb = ceil_div(ceil_div(K, GEMM_BK), split_k);
     int best = 128;
@@ -390,7 +390,10 @@ static int choose_bn(int M, int N, int K, int batches, int split_k) {
         if (bn > 32 && bn - 32 >= N) break;
         const long long tiles = (long long)ceil_div(N, bn) * mt * batches * split_k;
         const long long waves = (tiles + 147) / 148;
-        const double cost = (double)waves * (6.0 * 256 + (double)kb * (128 + bn) + 0.35 * bn * 4);
+        // latency policy: waves x per-CTA time; throughput policy (several clouds in flight share the SMs):
+        // total SM-time = tiles x per-CTA time, which favours wide tiles (fewer operand bytes per flop)
+        const double per_cta = 6.0 * 256 + (double)kb * (128 + bn) + 0.35 * bn * 4;
+        const double cost = throughput ? (double)tiles * per_cta : (double)waves * per_cta;
         if (cost < best_cost - 1e-9) best_cost = cost, best = bn;
     }
     return best;
@@ -421,7 +424,8 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     ep.bias = o->bias, ep.resid = o->resid, ep.alpha = o->alpha, ep.act = o->act, ep.accumulate = o->accumulate;
     ep.swiglu = o->swiglu;
     if (ep.swiglu && (ep.out_hi || !ep.out_f32 || ep.accumulate || ep.resid || ep.act || (sh.N & 1))) return PSAM_ERR_ARG;
-    int bn = choose_bn(sh.M, sh.N, sh.K, sh.nb1 * sh.nb2, sh.split_k);
+    int bn = choose_bn(sh.M, sh.N, sh.K, sh.nb1 * sh.nb2, sh.split_k, o->tile_hint == 1);
+    if (o->tile_hint >= 32 && o->tile_hint <= 256 && o->tile_hint % 32 == 0) bn = o->tile_hint;
     if (const char* e = getenv("PSAM_GEMM_BN")) {  // tuning override (tools/gemm_bench.py)
         const int v = atoi(e);
         if (v >= 32 && v <= 256 && v % 32 == 0) bn = v;

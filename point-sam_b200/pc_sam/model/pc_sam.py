@@ -86,6 +86,13 @@ class PointCloudSAM(nn.Module):
 
         return GraphPredictor(self, batch_size, num_points, num_prompts, multimask_output, use_graph)
 
+    def make_pipelined_predictor(self, batch_size: int, num_points: int, num_prompts: int, depth: int = 3,
+                                 multimask_output: bool = True, use_graph: bool = True):
+        """`depth` graph predictors on separate streams, used round-robin so consecutive clouds overlap."""
+        from psam_b200.predictor import PipelinedPredictor
+
+        return PipelinedPredictor(self, batch_size, num_points, num_prompts, depth, multimask_output, use_graph)
+
     # ------------------------------------------------------------------------------------------
     def predict_iterative(self, coords, features, prompt_coords_seq: List[torch.Tensor],
                           prompt_labels_seq: List[torch.Tensor]) -> List[Dict[str, torch.Tensor]]:

@@ -99,7 +99,12 @@ def nn_distance(query: torch.Tensor, key: torch.Tensor):
     return d
 
 
+GEMM_TILE_HINT = 0  # 0 = latency-optimal tiles, 1 = SM-time-optimal tiles (set by PipelinedPredictor)
+
+
 def gemm_raw(a: Operand, w: Operand, out: GemmOut, passes: int = 3, split_k: int = 1):
+    if out.tile_hint == 0:
+        out.tile_hint = GEMM_TILE_HINT
     nv.check(nv.lib().psam_gemm_bf16x3(byref(a), byref(w), byref(out), passes, split_k, nv.stream()), "gemm_bf16x3")
 
 

@@ -63,3 +63,68 @@ class GraphPredictor:
             else:
                 self.masks, self.iou = self._run()
         return self.masks, self.iou
+
+
+class PipelinedPredictor:
+    """Serving front-end: `depth` independent GraphPredictors (own stream, own CUDA graph, own static buffers,
+    shared weights) used round-robin, so consecutive clouds overlap on the GPU - cloud i+1's latency-bound FPS /
+    small kernels fill the SMs that cloud i's tile-starved GEMMs leave idle.  Each submit() returns a ticket;
+    result(ticket) waits for that cloud only."""
+
+    def __init__(self, model, B: int, N: int, P: int, depth: int = 3, multimask_output: bool = True, use_graph: bool = True):
+        self.lanes = [GraphPredictor(model, B, N, P, multimask_output, use_graph) for _ in range(depth)]
+        self.depth = depth
+        self.events = [torch.cuda.Event() for _ in range(depth)]
+        self.count = 0
+        self.host_out = None
+        import os
+
+        self.throughput_tiles = os.environ.get("PSAM_THROUGHPUT_TILES", "1") != "0"
+
+    def warmup(self, xyz, feats, pc, pl):
+        from . import ops
+
+        prev = ops.GEMM_TILE_HINT
+        if self.depth > 1 and self.throughput_tiles:
+            ops.GEMM_TILE_HINT = 1  # baked into the captured graphs
+        try:
+            for lane in self.lanes:
+                lane.warmup(xyz, feats, pc, pl)
+        finally:
+            ops.GEMM_TILE_HINT = prev
+
+    @property
+    def launches_per_step(self):
+        return self.lanes[0].launches_per_step
+
+    def enable_host_results(self, C: int):
+        """Pinned host buffers for the D2H of (mask logits, iou) per lane."""
+        B, N = self.lanes[0].xyz.shape[:2]
+        self.host_out = [(torch.empty((B, C, N), dtype=torch.float32).pin_memory(),
+                          torch.empty((B, C), dtype=torch.float32).pin_memory()) for _ in range(self.depth)]
+
+    def submit(self, xyz, feats, pc, pl, to_host: bool = False) -> int:
+        i = self.count % self.depth
+        lane = self.lanes[i]
+        masks, iou = lane(xyz, feats, pc, pl)
+        with torch.cuda.stream(lane.stream):
+            if to_host:
+                self.host_out[i][0].copy_(masks, non_blocking=True)
+                self.host_out[i][1].copy_(iou, non_blocking=True)
+            self.events[i].record()
+        self.count += 1
+        return self.count - 1
+
+    def result(self, ticket: int, to_host: bool = False):
+        i = ticket % self.depth
+        self.events[i].synchronize()
+        return self.host_out[i] if to_host else (self.lanes[i].masks, self.lanes[i].iou)
+
+    def wait_lane_free(self, ticket: int):
+        """Block until the lane that `ticket` will use has finished its previous cloud (host buffers reusable)."""
+        if ticket >= self.depth:
+            self.events[ticket % self.depth].synchronize()
+
+    def synchronize(self):
+        for lane in self.lanes:
+            lane.stream.synchronize()
