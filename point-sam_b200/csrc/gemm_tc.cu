@@ -53,6 +53,7 @@ struct GemmShape {
     int split_k;
     int passes;  // 1 or 3
     int bn;      // output-tile width actually used (multiple of 32, <= MAXBN)
+    int cm;      // cluster size along M (1, 2 or 4): the CTAs of a cluster share the W tile through TMA multicast
 };
 
 template <int MAXBN, int STAGES>
@@ -145,7 +146,7 @@ __device__ __forceinline__ void epi_rows_split(const float* __restrict__ stg, in
 template <int MAXBN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmShape shape, const GemmEpilogue ep) {
+               const __grid_constant__ CUtensorMap tmap_bmc, const GemmShape shape, const GemmEpilogue ep) {
     pdl_launch_dependents();
     using S = GemmSmem<MAXBN, STAGES>;
     extern __shared__ unsigned char smem_dyn[];
@@ -163,6 +164,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int bz = z / shape.split_k;
     const int b1 = bz % shape.nb1, b2 = bz / shape.nb1;
     const int BN = shape.bn;
+    const uint32_t cm = (uint32_t)shape.cm;                       // CTAs sharing the W tile (cluster along M)
+    const uint32_t crank = cm > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << cm) - 1u);
 
     const int kb_total = (shape.K + GEMM_BK - 1) / GEMM_BK;
     const int kb_per = (kb_total + shape.split_k - 1) / shape.split_k;
@@ -176,7 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tma_prefetch_desc(&tmap_b);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
-            mbar_init(smem_u32(&empty_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), cm);  // every CTA of the cluster writes into this stage
         }
         mbar_init(smem_u32(&tmem_full_bar), 1);
         fence_mbar_init();
@@ -186,6 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    if (cm > 1) cluster_sync_all();  // peers' barriers are initialised before any multicast / remote arrive
     pdl_wait();  // everything above is independent of the previous kernel; its outputs are read only below
 
     if (warp == 0) {
@@ -204,8 +209,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 if (lane == 0) {
                     mbar_arrive_expect_tx(fb, stage_bytes);
                     tma_load_5d(sa, &tmap_a, fb, k0, m_tile * GEMM_BM, 0, b1, b2);
-                } else {
+                } else if (cm == 1) {
                     tma_load_5d(sa + 2 * S::A_TILE, &tmap_b, fb, k0, n_tile * BN, 0, b1, b2);
+                } else {
+                    // this CTA fetches rows [crank*BN/cm, (crank+1)*BN/cm) of the W tile once and multicasts them
+                    // into the same stage of every CTA of the cluster (hi and lo planes separately)
+                    const int rows = BN / (int)cm;
+                    const uint32_t off = crank * (uint32_t)rows * 128u;
+                    tma_load_5d_mc(sa + 2 * S::A_TILE + off, &tmap_bmc, fb, k0, n_tile * BN + (int)crank * rows, 0, b1, b2, cmask);
+                    if (lo_pass)
+                        tma_load_5d_mc(sa + 2 * S::A_TILE + BN * GEMM_BK * 2 + off, &tmap_bmc, fb, k0, n_tile * BN + (int)crank * rows, 1, b1, b2, cmask);
                 }
             }
         }
@@ -240,7 +253,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                         umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
                     }
                 }
-                umma_commit(smem_u32(&empty_bar[s]));                        // stage reusable once these MMAs retire
+                if (cm > 1) umma_commit_mc(smem_u32(&empty_bar[s]), cmask);  // release the stage in every CTA of the cluster
+                else umma_commit(smem_u32(&empty_bar[s]));                   // stage reusable once these MMAs retire
                 if (i == num_kb - 1) umma_commit(smem_u32(&tmem_full_bar));  // accumulator complete
             }
             __syncwarp();
@@ -318,6 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
+    if (cm > 1) cluster_sync_all();  // no CTA leaves while peers can still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, S::TMEM_COLS);
@@ -368,13 +383,34 @@ int make_operand_map_ext(CUtensorMap* map, const psam_operand* op, int box_rows,
 }
 
 template <int MAXBN, int STAGES>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& sh, const GemmEpilogue& ep,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbmc, const GemmShape& sh,
+                       const GemmEpilogue& ep, cudaStream_t stream) {
     auto kern = gemm_tc_kernel<MAXBN, STAGES>;
     using S = GemmSmem<MAXBN, STAGES>;
     PSAM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    dim3 grid((unsigned)ceil_div(sh.N, sh.bn), (unsigned)ceil_div(sh.M, GEMM_BM), (unsigned)(sh.nb1 * sh.nb2 * sh.split_k));
-    PSAM_CUDA_TRY(psam::launch(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)(S::TOTAL), stream, ma, mb, sh, ep));
+    const int mt = ceil_div(ceil_div(sh.M, GEMM_BM), sh.cm) * sh.cm;  // pad the m-tiles to whole clusters
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ceil_div(sh.N, sh.bn), (unsigned)mt, (unsigned)(sh.nb1 * sh.nb2 * sh.split_k));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (sh.cm > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1;
+        attr[na].val.clusterDim.y = (unsigned)sh.cm;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    PSAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma, mb, mbmc, sh, ep));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -431,13 +467,28 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
         if (v >= 32 && v <= 256 && v % 32 == 0) bn = v;
     }
     sh.bn = bn;
-    CUtensorMap ma, mb;
+    // CTAs of consecutive m-tiles form a cluster and share each W tile through TMA multicast
+    const int mtiles = ceil_div(sh.M, GEMM_BM);
+    // MEASURED (B200, config c2, 8 clouds in flight): cluster 4 -> 581 clouds/s, no cluster -> 626 clouds/s: the L2
+    // already merges the concurrent requests of the 4 m-tile CTAs for the same W lines, and the cluster couples their
+    // progress.  Multicast therefore stays opt-in (PSAM_GEMM_CLUSTER=2|4).
+    int cm = 1;
+    if (const char* e = getenv("PSAM_GEMM_CLUSTER")) {
+        const int v = atoi(e);
+        const int cap = mtiles >= 4 ? 4 : (mtiles >= 2 ? 2 : 1);
+        if (v == 1 || v == 2 || v == 4) cm = v < cap ? v : cap;
+    }
+    while (cm > 1 && (bn / cm) % 8) cm /= 2;
+    sh.cm = cm;
+    CUtensorMap ma, mb, mbmc;
     int rc = make_operand_map(&ma, a, GEMM_BM, passes == 3 ? 2 : 1);
     if (rc) return rc;
     rc = make_operand_map(&mb, w, bn, passes == 3 ? 2 : 1);
     if (rc) return rc;
-    if (bn <= 64) return launch_gemm<64, 4>(ma, mb, sh, ep, stream);
-    if (bn <= 128) return launch_gemm<128, 3>(ma, mb, sh, ep, stream);
-    if (bn <= 160) return launch_gemm<160, 3>(ma, mb, sh, ep, stream);
-    return launch_gemm<256, 2>(ma, mb, sh, ep, stream);
+    rc = make_operand_map(&mbmc, w, bn / cm, 1);
+    if (rc) return rc;
+    if (bn <= 64) return launch_gemm<64, 4>(ma, mb, mbmc, sh, ep, stream);
+    if (bn <= 128) return launch_gemm<128, 3>(ma, mb, mbmc, sh, ep, stream);
+    if (bn <= 160) return launch_gemm<160, 3>(ma, mb, mbmc, sh, ep, stream);
+    return launch_gemm<256, 2>(ma, mb, mbmc, sh, ep, stream);
 }

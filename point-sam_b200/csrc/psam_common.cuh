@@ -207,6 +207,16 @@ __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void* tmap,
         : "memory");
 }
 
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and each of those
+// CTAs' mbarrier (same CTA-relative offset) receives the complete_tx for the bytes written into it
+__device__ __forceinline__ void tma_load_5d_mc(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
+                                               int c3, int c4, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+        ::"r"(smem_dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(cta_mask)
+        : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ---------------------------------------------------------------------------------------------
@@ -235,6 +245,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// same, arriving on the mbarrier at this CTA-relative offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
 // 32 lanes x 32 columns of fp32 accumulators: thread t of the warp receives row (lane base + t).

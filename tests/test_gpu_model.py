@@ -128,3 +128,23 @@ def test_demo_api_and_errors():
     model.pc_encoder.patch_embed.grouper.group_size = 8
     m3, _ = model.predict_masks(xyz.to(d), feats.to(d), pc.to(d), pl.to(d))
     assert m3.shape == (1, 3, 1500)
+
+
+def test_config4_shapes_vs_cpu_oracle():
+    """BASELINE config[3] geometry (N=131072, group_number=2048, group_size=256, KITTI-shaped cloud) with the tiny
+    encoder: exercises the streaming FPS plan (cloud larger than a cluster's registers), kNN with K=256 over 131072
+    keys, the unfused tensor-core attention path (2048 tokens > 512) and the 131072-point upsampling."""
+    model, oracle = _build("eva02_test_tiny", 2048, 256, 77)
+    xyz, feats = synth.make_batch(1, 131072, 5, "kitti")
+    pc, pl = synth.make_prompts(xyz, 2, 5)
+    d = torch.device("cuda:0")
+    with torch.no_grad():
+        want_m, want_i = oracle.predict_masks(xyz, feats, pc, pl, None, True)
+        got_m, got_i = model.predict_masks(xyz.to(d), feats.to(d), pc.to(d), pl.to(d), None, True)
+        _, patches = model.pc_encoder(xyz.to(d), feats.to(d))
+    from oracle import tokenizer_ref
+
+    assert np.array_equal(patches["fps_idx"].cpu().numpy(), tokenizer_ref.fps(xyz.numpy(), 2048))
+    _report("c4-shape masks", got_m.cpu(), want_m)
+    np.testing.assert_allclose(got_m.cpu().numpy(), want_m.numpy(), atol=ATOL, rtol=RTOL)
+    np.testing.assert_allclose(got_i.cpu().numpy(), want_i.numpy(), atol=ATOL, rtol=RTOL)
