@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -168,8 +168,8 @@ class ProfilingLib:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=240)
+    ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--config", default="c2")
     ap.add_argument("--no-graph", action="store_true")
@@ -245,12 +245,11 @@ def main():
     def step_dev(i):
         pp.submit(*devin[i % n_rot])
 
-    timed(step_dev, args.warmup)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # samples clocks / throttle reasons over the warm-up and both timed arms
+    timed(step_dev, args.warmup)
     ms_dev = timed(step_dev, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
 
     # single-stream latency of one cloud (no overlap between clouds), for the record
     def step_single(i):
@@ -265,6 +264,7 @@ def main():
 
     timed(step_e2e, args.warmup)
     ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
     out_m, out_i = pp.host_out[0]
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     d2h = out_m.numel() * 4 + out_i.numel() * 4
