@@ -143,6 +143,79 @@ __device__ __forceinline__ void epi_rows_split(const float* __restrict__ stg, in
     }
 }
 
+
+// Shared epilogue of the 1-CTA and 2-CTA kernels: TMEM -> registers (thread = row) -> per-warp smem transpose ->
+// coalesced global accesses (lane = column: every store/load/red touches one contiguous 128-byte row segment).
+__device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const GemmEpilogue& ep, unsigned char* smem_aligned,
+                                              uint32_t tmem_base, uint32_t tmem_full_bar_addr, int warp, int lane, int m_tile,
+                                              int n_tile, int b1, int b2, int split, int num_kb, int BN) {
+        const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+        const int row0 = m_tile * GEMM_BM + quarter * 32;
+        if (num_kb > 0) {
+            mbar_wait(tmem_full_bar_addr, 0);
+            tc_fence_after();
+        }
+        // All TMA loads have landed and all MMAs have retired: the pipeline stages are free to reuse.
+        float* stg = reinterpret_cast<float*>(smem_aligned) + (warp - 2) * (32 * 33);
+        const int ehalf = (warp - 2) >> 2;  // the warps of a lane quarter take interleaved 32-column chunks
+        const long long obase = (long long)b1 * ep.out_b1 + (long long)b2 * ep.out_b2;
+        float* out = ep.out_f32 ? ep.out_f32 + obase : nullptr;
+        const float* res = (ep.resid && !ep.accumulate) ? ep.resid + obase : nullptr;
+        __nv_bfloat16* ohi = ep.out_hi ? ep.out_hi + (long long)b1 * ep.outs_b1 + (long long)b2 * ep.outs_b2 : nullptr;
+        const bool add_bias = ep.bias && split == 0;
+        const int nchunks = BN / 32;
+#pragma unroll 1
+        for (int c = ehalf; c < nchunks; c += GEMM_EPI_PER_QUARTER) {
+            const int col0 = n_tile * BN + c * 32;
+            if (col0 >= shape.N) break;
+            uint32_t v[32];
+            if (num_kb > 0) {
+                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) v[t] = 0u;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) stg[lane * 33 + t] = __uint_as_float(v[t]);
+            __syncwarp();
+            const int col = col0 + lane;
+            const bool col_ok = col < shape.N;
+            if (ohi == nullptr) {
+                const float bv = (add_bias && col_ok) ? ep.bias[col] : 0.f;
+#define PSAM_EPI_F32(A, R, C) epi_rows_f32<A, R, C>(stg, lane, row0, shape.M, col, col_ok, ep.alpha, bv, out, res, ep.ldo)
+                if (ep.swiglu) epi_rows_swiglu(stg, lane, row0, shape.M, col, col_ok, ep.alpha, bv, out, ep.ldo);
+                else if (ep.accumulate) PSAM_EPI_F32(ACT_NONE, false, true);
+                else if (res) {
+                    if (ep.act == ACT_NONE) PSAM_EPI_F32(ACT_NONE, true, false);
+                    else if (ep.act == ACT_GELU) PSAM_EPI_F32(ACT_GELU, true, false);
+                    else PSAM_EPI_F32(ACT_RELU, true, false);
+                } else {
+                    if (ep.act == ACT_NONE) PSAM_EPI_F32(ACT_NONE, false, false);
+                    else if (ep.act == ACT_GELU) PSAM_EPI_F32(ACT_GELU, false, false);
+                    else PSAM_EPI_F32(ACT_RELU, false, false);
+                }
+#undef PSAM_EPI_F32
+            } else {
+                const float* bias = add_bias ? ep.bias : nullptr;
+                const bool va = ((ep.ldo_s | ep.out_plane | ep.outs_b1 | ep.outs_b2) & 1) == 0;
+#define PSAM_EPI_SP(A, R, F) epi_rows_split<A, R, F>(stg, lane, row0, shape.M, shape.N, col0, ep.alpha, bias, out, res, ep.ldo, ohi, ep.out_plane, ep.ldo_s, va)
+#define PSAM_EPI_SP_ACT(R, F)                                   \
+    if (ep.act == ACT_NONE) PSAM_EPI_SP(ACT_NONE, R, F);        \
+    else if (ep.act == ACT_GELU) PSAM_EPI_SP(ACT_GELU, R, F);   \
+    else PSAM_EPI_SP(ACT_RELU, R, F)
+                if (res) {
+                    if (out) { PSAM_EPI_SP_ACT(true, true); } else { PSAM_EPI_SP_ACT(true, false); }
+                } else {
+                    if (out) { PSAM_EPI_SP_ACT(false, true); } else { PSAM_EPI_SP_ACT(false, false); }
+                }
+#undef PSAM_EPI_SP_ACT
+#undef PSAM_EPI_SP
+            }
+        }
+}
+
 template <int MAXBN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -263,71 +336,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ===================== epilogue (warps 2..9) =====================
         // TMEM -> registers (thread = row) -> per-warp smem transpose -> coalesced global accesses
         // (lane = column: every store/load/red instruction touches one contiguous 128-byte row segment).
-        const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
-        const int row0 = m_tile * GEMM_BM + quarter * 32;
-        if (num_kb > 0) {
-            mbar_wait(smem_u32(&tmem_full_bar), 0);
-            tc_fence_after();
-        }
-        // All TMA loads have landed and all MMAs have retired: the pipeline stages are free to reuse.
-        float* stg = reinterpret_cast<float*>(smem_aligned) + (warp - 2) * (32 * 33);
-        const int ehalf = (warp - 2) >> 2;  // the warps of a lane quarter take interleaved 32-column chunks
-        const long long obase = (long long)b1 * ep.out_b1 + (long long)b2 * ep.out_b2;
-        float* out = ep.out_f32 ? ep.out_f32 + obase : nullptr;
-        const float* res = (ep.resid && !ep.accumulate) ? ep.resid + obase : nullptr;
-        __nv_bfloat16* ohi = ep.out_hi ? ep.out_hi + (long long)b1 * ep.outs_b1 + (long long)b2 * ep.outs_b2 : nullptr;
-        const bool add_bias = ep.bias && split == 0;
-        const int nchunks = BN / 32;
-#pragma unroll 1
-        for (int c = ehalf; c < nchunks; c += GEMM_EPI_PER_QUARTER) {
-            const int col0 = n_tile * BN + c * 32;
-            if (col0 >= shape.N) break;
-            uint32_t v[32];
-            if (num_kb > 0) {
-                tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int t = 0; t < 32; ++t) v[t] = 0u;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int t = 0; t < 32; ++t) stg[lane * 33 + t] = __uint_as_float(v[t]);
-            __syncwarp();
-            const int col = col0 + lane;
-            const bool col_ok = col < shape.N;
-            if (ohi == nullptr) {
-                const float bv = (add_bias && col_ok) ? ep.bias[col] : 0.f;
-#define PSAM_EPI_F32(A, R, C) epi_rows_f32<A, R, C>(stg, lane, row0, shape.M, col, col_ok, ep.alpha, bv, out, res, ep.ldo)
-                if (ep.swiglu) epi_rows_swiglu(stg, lane, row0, shape.M, col, col_ok, ep.alpha, bv, out, ep.ldo);
-                else if (ep.accumulate) PSAM_EPI_F32(ACT_NONE, false, true);
-                else if (res) {
-                    if (ep.act == ACT_NONE) PSAM_EPI_F32(ACT_NONE, true, false);
-                    else if (ep.act == ACT_GELU) PSAM_EPI_F32(ACT_GELU, true, false);
-                    else PSAM_EPI_F32(ACT_RELU, true, false);
-                } else {
-                    if (ep.act == ACT_NONE) PSAM_EPI_F32(ACT_NONE, false, false);
-                    else if (ep.act == ACT_GELU) PSAM_EPI_F32(ACT_GELU, false, false);
-                    else PSAM_EPI_F32(ACT_RELU, false, false);
-                }
-#undef PSAM_EPI_F32
-            } else {
-                const float* bias = add_bias ? ep.bias : nullptr;
-                const bool va = ((ep.ldo_s | ep.out_plane | ep.outs_b1 | ep.outs_b2) & 1) == 0;
-#define PSAM_EPI_SP(A, R, F) epi_rows_split<A, R, F>(stg, lane, row0, shape.M, shape.N, col0, ep.alpha, bias, out, res, ep.ldo, ohi, ep.out_plane, ep.ldo_s, va)
-#define PSAM_EPI_SP_ACT(R, F)                                   \
-    if (ep.act == ACT_NONE) PSAM_EPI_SP(ACT_NONE, R, F);        \
-    else if (ep.act == ACT_GELU) PSAM_EPI_SP(ACT_GELU, R, F);   \
-    else PSAM_EPI_SP(ACT_RELU, R, F)
-                if (res) {
-                    if (out) { PSAM_EPI_SP_ACT(true, true); } else { PSAM_EPI_SP_ACT(true, false); }
-                } else {
-                    if (out) { PSAM_EPI_SP_ACT(false, true); } else { PSAM_EPI_SP_ACT(false, false); }
-                }
-#undef PSAM_EPI_SP_ACT
-#undef PSAM_EPI_SP
-            }
-        }
+        gemm_epilogue(shape, ep, smem_aligned, tmem_base, smem_u32(&tmem_full_bar), warp, lane, m_tile, n_tile, b1, b2, split, num_kb, BN);
     }
 
     tc_fence_before();
@@ -336,6 +345,160 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, S::TMEM_COLS);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// 2-CTA variant (tcgen05 cta_group::2): two CTAs of a cluster (consecutive m-tiles) act as one 256 x BN MMA.
+// Each CTA streams its own 128 A rows and only HALF of the W tile (BN/2 rows); the tensor cores of the pair read
+// both halves, so the operand bytes ingested per SM and flop drop by 1/3 (BN=256: 64 KB instead of 96 KB per
+// 64-deep k-block) - the quantity that bounds this GEMM (profiles/r01_gemm_qkv_ncu_full.md).
+//   * TMEM is allocated/deallocated by warp 1 of BOTH CTAs with cta_group::2,
+//   * both producers signal the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2),
+//   * only the leader issues tcgen05.mma.cta_group::2; its commits are multicast to both CTAs' barriers,
+//   * each CTA runs the shared epilogue on its own 128 accumulator rows.
+// ---------------------------------------------------------------------------------------------
+template <int MAXBN, int STAGES>
+struct Gemm2Smem {
+    static constexpr int A_TILE = GEMM_BM * GEMM_BK * 2;
+    static constexpr int BH_TILE = (MAXBN / 2) * GEMM_BK * 2;  // this CTA's half of the W tile, one plane
+    static constexpr int STAGE = 2 * A_TILE + 2 * BH_TILE;
+    static constexpr int TOTAL = STAGES * STAGE + 1024;
+    static constexpr int TMEM_COLS = MAXBN <= 64 ? 64 : (MAXBN <= 128 ? 128 : 256);
+};
+
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t smem_dst, const void* tmap, uint32_t leader_bar, int c0, int c1, int c2,
+                                                int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_dst), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {  // arrives on `bar` in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <int MAXBN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_bh, const GemmShape shape,
+                const GemmEpilogue ep) {
+    pdl_launch_dependents();
+    using S = Gemm2Smem<MAXBN, STAGES>;
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];   // used in the leader CTA only
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y;  // the CTA pair must be adjacent in the cluster x dimension
+    const int z = blockIdx.z;
+    const int split = z % shape.split_k;
+    const int bz = z / shape.split_k;
+    const int b1 = bz % shape.nb1, b2 = bz / shape.nb1;
+    const int BN = shape.bn, BNH = shape.bn / 2;
+    const uint32_t crank = cluster_ctarank();  // 0 = leader of the pair
+    const bool leader = crank == 0;
+
+    const int kb_total = (shape.K + GEMM_BK - 1) / GEMM_BK;
+    const int kb_per = (kb_total + shape.split_k - 1) / shape.split_k;
+    const int kb_begin = split * kb_per;
+    const int kb_end = min(kb_total, kb_begin + kb_per);
+    const int num_kb = max(0, kb_end - kb_begin);
+    const bool lo_pass = shape.passes == 3;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_bh);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)S::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    cluster_sync_all();  // both CTAs' barriers and TMEM are ready before any cross-CTA signal
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===================== TMA producers (both CTAs) =====================
+        if (lane < 2) {
+            const uint32_t cta_bytes = (lo_pass ? 2u : 1u) * (uint32_t)(S::A_TILE + BNH * GEMM_BK * 2);
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                const uint32_t fb_leader = mapa_shared(smem_u32(&full_bar[s]), 0);  // the leader's barrier collects both CTAs' bytes
+                const uint32_t sa = smem_base + s * S::STAGE;
+                const int k0 = (kb_begin + i) * GEMM_BK;
+                if (lane == 0) {
+                    if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[s]), 2u * cta_bytes);
+                    tma_load_5d_2sm(sa, &tmap_a, fb_leader, k0, m_tile * GEMM_BM, 0, b1, b2);
+                } else {
+                    tma_load_5d_2sm(sa + 2 * S::A_TILE, &tmap_bh, fb_leader, k0, n_tile * BN + (int)crank * BNH, 0, b1, b2);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_base + s * S::STAGE;
+                    const uint64_t a_hi = umma_desc_k_sw128(sa);
+                    const uint64_t a_lo = umma_desc_k_sw128(sa + S::A_TILE);
+                    const uint64_t b_hi = umma_desc_k_sw128(sa + 2 * S::A_TILE);
+                    const uint64_t b_lo = umma_desc_k_sw128(sa + 2 * S::A_TILE + BNH * GEMM_BK * 2);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_2sm(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    if (lo_pass) {
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_2sm(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16_2sm(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                    }
+                    umma_commit_2sm(smem_u32(&empty_bar[s]));
+                    if (i == num_kb - 1) umma_commit_2sm(smem_u32(&tmem_full_bar));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        gemm_epilogue(shape, ep, smem_aligned, tmem_base, smem_u32(&tmem_full_bar), warp, lane, m_tile, n_tile, b1, b2, split, num_kb, BN);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS) : "memory");
     }
 }
 
@@ -415,6 +578,36 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
     return PSAM_OK;
 }
 
+template <int MAXBN, int STAGES>
+static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mbh, const GemmShape& sh, const GemmEpilogue& ep,
+                        cudaStream_t stream) {
+    auto kern = gemm_tc2_kernel<MAXBN, STAGES>;
+    using S = Gemm2Smem<MAXBN, STAGES>;
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    const int mt = ceil_div(ceil_div(sh.M, GEMM_BM), 2) * 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)mt, (unsigned)ceil_div(sh.N, sh.bn), (unsigned)(sh.nb1 * sh.nb2 * sh.split_k));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;  // cta_group::2 pairs are the CTAs with consecutive ranks along x
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    int na = 1;
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    PSAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, ma, mbh, sh, ep));
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
 // Output-tile width: multiple of 32 in [32, 256] minimising (waves over 148 SMs) x (per-CTA cost), where the
 // per-CTA cost follows the operand bytes streamed per k-block (the kernel is L2->SM bandwidth bound).
 static int choose_bn(int M, int N, int K, int batches, int split_k, bool throughput) {
@@ -467,8 +660,26 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
         if (v >= 32 && v <= 256 && v % 32 == 0) bn = v;
     }
     sh.bn = bn;
-    // CTAs of consecutive m-tiles form a cluster and share each W tile through TMA multicast
     const int mtiles = ceil_div(sh.M, GEMM_BM);
+    // 2-CTA path (cta_group::2): pairs of m-tiles, each CTA streams half of the W tile.  PSAM_GEMM_2CTA=1|0 forces it.
+    {
+        int use2 = 0;
+        if (const char* e = getenv("PSAM_GEMM_2CTA")) use2 = atoi(e);
+        if (use2 && mtiles >= 2 && sh.N >= 128) {
+            int bn2 = (o->tile_hint == 1 || sh.N >= 256) ? 256 : 128;
+            if (o->tile_hint >= 64 && o->tile_hint <= 256 && o->tile_hint % 64 == 0) bn2 = o->tile_hint;
+            if (bn2 > 128 && (long long)ceil_div(sh.N, 256) * ceil_div(mtiles, 2) * sh.nb1 * sh.nb2 * sh.split_k * 2 < 100 && o->tile_hint != 1) bn2 = 128;
+            sh.bn = bn2;
+            sh.cm = 2;
+            CUtensorMap ma2, mbh;
+            int rc2 = make_operand_map(&ma2, a, GEMM_BM, passes == 3 ? 2 : 1);
+            if (rc2) return rc2;
+            rc2 = make_operand_map(&mbh, w, bn2 / 2, passes == 3 ? 2 : 1);
+            if (rc2) return rc2;
+            return bn2 <= 128 ? launch_gemm2<128, 4>(ma2, mbh, sh, ep, stream) : launch_gemm2<256, 3>(ma2, mbh, sh, ep, stream);
+        }
+    }
+    // CTAs of consecutive m-tiles form a cluster and share each W tile through TMA multicast
     // MEASURED (B200, config c2, 8 clouds in flight): cluster 4 -> 581 clouds/s, no cluster -> 626 clouds/s: the L2
     // already merges the concurrent requests of the 4 m-tile CTAs for the same W lines, and the cluster couples their
     // progress.  Multicast therefore stays opt-in (PSAM_GEMM_CLUSTER=2|4).
