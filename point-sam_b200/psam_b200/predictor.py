@@ -26,6 +26,18 @@ class GraphPredictor:
         self.stream = torch.cuda.Stream(device=d)
 
     def _run(self):
+        import os
+
+        only = os.environ.get("PSAM_PROFILE_STAGE")  # attribution experiments only (tools/stage_attribution.sh)
+        if only == "tokenizer":
+            from . import engine as _e
+
+            p = _e.run_knn_grouper(self.model.pc_encoder.patch_embed.grouper, self.xyz, self.feats)
+            emb = _e.run_patch_encoder(self.model.pc_encoder.patch_embed.patch_encoder, p["features"])
+            return emb, emb
+        if only == "encoder":
+            enc = self.model._encode(self.xyz, self.feats)
+            return enc["pc_embeddings"], enc["pc_pe"]
         enc = self.model._encode(self.xyz, self.feats)
         sparse = engine.run_point_encoder(self.model.point_encoder, self.pc, self.pl, check=False)
         dense = self.model.mask_encoder(None, self.xyz, enc["patches"]["centers"], enc["patches"]["knn_idx"])
