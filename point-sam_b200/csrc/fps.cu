@@ -212,7 +212,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long 
 
 template <int PPT>
 static int launch_fps(const float* xyz, int B, int N, int G, int log2T, long long* idx, float* centers, float* ws,
-                      int cluster, cudaStream_t stream) {
+                      int cluster, cudaStream_t stream, bool probe_only = false) {
     auto kern = fps_cluster_kernel<PPT>;
     if (cluster > 8) PSAM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
@@ -229,13 +229,22 @@ static int launch_fps(const float* xyz, int B, int N, int G, int log2T, long lon
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    if (probe_only) {  // can a cluster of this size be co-scheduled at all on this device?
+        int n = 0;
+        cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            return PSAM_ERR_UNSUPPORTED;
+        }
+        return n > 0 ? PSAM_OK : PSAM_ERR_UNSUPPORTED;
+    }
     PSAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, xyz, N, G, log2T, idx, centers, ws));
     return PSAM_OK;
 }
 
 static void fps_plan(int N, int max_cluster, int* cluster, int* ppt) {
     // Prefer the largest cluster (least work per SM), then the smallest PPT that holds the cloud.
-    int c = max_cluster;
+    int c = max_cluster > 8 && N > 8 * FPS_THREADS * 32 ? max_cluster : (max_cluster > 8 ? 8 : max_cluster);
     while (c > 1 && (c / 2) * FPS_THREADS >= N) c /= 2;
     long long per_thread = ceil_div_ll(N, (long long)c * FPS_THREADS);
     int p = 1;
@@ -244,10 +253,19 @@ static void fps_plan(int N, int max_cluster, int* cluster, int* ppt) {
     *ppt = (p <= 32) ? p : 0;
 }
 
+// 16-CTA clusters are "non-portable": probed once per process, used only for clouds that do not fit 8 CTAs' registers.
+static int fps_max_cluster() {
+    static int v = 0;
+    if (v == 0) v = launch_fps<32>(nullptr, 1, 1, 1, 5, nullptr, nullptr, nullptr, 16, 0, true) == PSAM_OK ? 16 : 8;
+    return v;
+}
+
 }  // namespace psam
 
 extern "C" size_t psam_fps_workspace_bytes(int B, int N, int G) {
     (void)G;
+    // conservative: the 16-CTA register-resident plan may be unavailable on the device, so every cloud beyond the
+    // 8-CTA capacity gets a workspace (used only by the streaming fallback)
     int cluster, ppt;
     psam::fps_plan(N, 8, &cluster, &ppt);
     return ppt == 0 ? (size_t)B * N * sizeof(float) : 0;
@@ -264,7 +282,8 @@ extern "C" int psam_fps_f32(const float* xyz, int B, int N, int G, long long* id
     int log2T = 0;
     while ((1 << log2T) < T) ++log2T;
     int cluster, ppt;
-    fps_plan(N, 8, &cluster, &ppt);
+    fps_plan(N, N > 8 * FPS_THREADS * 32 ? fps_max_cluster() : 8, &cluster, &ppt);
+    if (ppt == 0) cluster = fps_max_cluster();  // streaming fallback: spread the cloud over as many SMs as possible
     if (ppt == 0 && !workspace) return PSAM_ERR_ARG;
     float* ws = (float*)workspace;
     switch (ppt) {
