@@ -148,3 +148,31 @@ def test_config4_shapes_vs_cpu_oracle():
     _report("c4-shape masks", got_m.cpu(), want_m)
     np.testing.assert_allclose(got_m.cpu().numpy(), want_m.numpy(), atol=ATOL, rtol=RTOL)
     np.testing.assert_allclose(got_i.cpu().numpy(), want_i.numpy(), atol=ATOL, rtol=RTOL)
+
+
+def test_graph_and_pipelined_predictors_match_eager():
+    """CUDA-graph replay and the multi-stream pipelined front-end return the same logits as the eager call."""
+    model, _ = _build("eva02_test_tiny", 64, 16, 11)
+    d = torch.device("cuda:0")
+    clouds = [synth.make_batch(1, 2048, s) for s in (1, 2, 3, 4, 5)]
+    prompts = [synth.make_prompts(c[0], 1, s) for s, c in enumerate(clouds)]
+    want = []
+    with torch.no_grad():
+        for (xyz, feats), (pc, pl) in zip(clouds, prompts):
+            m, i = model.predict_masks(xyz.to(d), feats.to(d), pc.to(d), pl.to(d), None, True)
+            want.append((m.cpu(), i.cpu()))
+    pp = model.make_pipelined_predictor(1, 2048, 1, depth=3)
+    pp.warmup(*[t.to(d) for t in (*clouds[0], *prompts[0])])
+    pp.enable_host_results(3)
+    tickets = []
+    for (xyz, feats), (pc, pl) in zip(clouds, prompts):
+        pp.wait_lane_free(pp.count)
+        if pp.count >= pp.depth:  # the host consumes the lane's previous result before the lane is reused
+            t_old = pp.count - pp.depth
+            m, i = pp.result(t_old, to_host=True)
+            torch.testing.assert_close(m, want[t_old][0], atol=2e-5, rtol=1e-4)
+        tickets.append(pp.submit(xyz.pin_memory(), feats.pin_memory(), pc.pin_memory(), pl.pin_memory(), to_host=True))
+    for t in tickets[-pp.depth:]:
+        m, i = pp.result(t, to_host=True)
+        torch.testing.assert_close(m, want[t][0], atol=2e-5, rtol=1e-4)
+        torch.testing.assert_close(i, want[t][1], atol=2e-5, rtol=1e-4)
