@@ -56,10 +56,10 @@ struct GemmShape {
     int cm;      // cluster size along M (1, 2 or 4): the CTAs of a cluster share the W tile through TMA multicast
 };
 
-template <int MAXBN, int STAGES>
+template <int MAXBN, int STAGES, int BK = 64>
 struct GemmSmem {
-    static constexpr int A_TILE = GEMM_BM * GEMM_BK * 2;  // bytes per plane
-    static constexpr int B_TILE = MAXBN * GEMM_BK * 2;
+    static constexpr int A_TILE = GEMM_BM * BK * 2;  // bytes per plane
+    static constexpr int B_TILE = MAXBN * BK * 2;
     static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
     static constexpr int TOTAL = STAGES * STAGE + 1024;  // + alignment slack
     static constexpr int TMEM_COLS = MAXBN <= 64 ? 64 : (MAXBN <= 128 ? 128 : 256);
@@ -144,6 +144,19 @@ __device__ __forceinline__ void epi_rows_split(const float* __restrict__ stg, in
 }
 
 
+// K-major shared-memory matrix descriptor for a tile whose rows hold BK bf16: BK=64 -> 128-byte rows / SWIZZLE_128B
+// (8-row groups 1024 B apart), BK=32 -> 64-byte rows / SWIZZLE_64B (8-row groups 512 B apart).
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
+    if (BK == 64) return umma_desc_k_sw128(smem_addr);
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(512 >> 4) << 32;  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;           // descriptor version (sm_100)
+    d |= (uint64_t)4 << 61;           // layout type SWIZZLE_64B
+    return d;
+}
+
 // Shared epilogue of the 1-CTA and 2-CTA kernels: TMEM -> registers (thread = row) -> per-warp smem transpose ->
 // coalesced global accesses (lane = column: every store/load/red touches one contiguous 128-byte row segment).
 __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const GemmEpilogue& ep, unsigned char* smem_aligned,
@@ -216,12 +229,14 @@ __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const Gemm
         }
 }
 
-template <int MAXBN, int STAGES>
+// BK = 64: rows of 128 B, SWIZZLE_128B.  BK = 32: rows of 64 B, SWIZZLE_64B - half-size stages, twice as many of them
+// in flight (finer-grained pipeline; the wide-tile throughput configuration otherwise has only 2 stages).
+template <int MAXBN, int STAGES, int BK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_bmc, const GemmShape shape, const GemmEpilogue ep) {
     pdl_launch_dependents();
-    using S = GemmSmem<MAXBN, STAGES>;
+    using S = GemmSmem<MAXBN, STAGES, BK>;
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -241,7 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t crank = cm > 1 ? cluster_ctarank() : 0u;
     const uint16_t cmask = (uint16_t)((1u << cm) - 1u);
 
-    const int kb_total = (shape.K + GEMM_BK - 1) / GEMM_BK;
+    const int kb_total = (shape.K + BK - 1) / BK;
     const int kb_per = (kb_total + shape.split_k - 1) / shape.split_k;
     const int kb_begin = split * kb_per;
     const int kb_end = min(kb_total, kb_begin + kb_per);
@@ -271,14 +286,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // lane 0 streams the A tiles, lane 1 the W tiles; the hi and lo planes of a tile arrive with ONE
         // 3-D box (64 x rows x 2 planes) - TMA cost is dominated by a fixed per-operation overhead.
         if (lane < 2) {
-            const uint32_t stage_bytes = (lo_pass ? 2u : 1u) * (uint32_t)(S::A_TILE + BN * GEMM_BK * 2);
+            const uint32_t stage_bytes = (lo_pass ? 2u : 1u) * (uint32_t)(S::A_TILE + BN * BK * 2);
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
                 mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
                 const uint32_t fb = smem_u32(&full_bar[s]);
                 const uint32_t sa = smem_base + s * S::STAGE;
-                const int k0 = (kb_begin + i) * GEMM_BK;
+                const int k0 = (kb_begin + i) * BK;
                 if (lane == 0) {
                     mbar_arrive_expect_tx(fb, stage_bytes);
                     tma_load_5d(sa, &tmap_a, fb, k0, m_tile * GEMM_BM, 0, b1, b2);
@@ -291,7 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const uint32_t off = crank * (uint32_t)rows * 128u;
                     tma_load_5d_mc(sa + 2 * S::A_TILE + off, &tmap_bmc, fb, k0, n_tile * BN + (int)crank * rows, 0, b1, b2, cmask);
                     if (lo_pass)
-                        tma_load_5d_mc(sa + 2 * S::A_TILE + BN * GEMM_BK * 2 + off, &tmap_bmc, fb, k0, n_tile * BN + (int)crank * rows, 1, b1, b2, cmask);
+                        tma_load_5d_mc(sa + 2 * S::A_TILE + BN * BK * 2 + off, &tmap_bmc, fb, k0, n_tile * BN + (int)crank * rows, 1, b1, b2, cmask);
                 }
             }
         }
@@ -305,23 +320,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t sa = smem_base + s * S::STAGE;
-                const uint64_t a_hi = umma_desc_k_sw128(sa);
-                const uint64_t a_lo = umma_desc_k_sw128(sa + S::A_TILE);
-                const uint64_t b_hi = umma_desc_k_sw128(sa + 2 * S::A_TILE);
-                const uint64_t b_lo = umma_desc_k_sw128(sa + 2 * S::A_TILE + BN * GEMM_BK * 2);
+                const uint64_t a_hi = umma_desc_k<BK>(sa);
+                const uint64_t a_lo = umma_desc_k<BK>(sa + S::A_TILE);
+                const uint64_t b_hi = umma_desc_k<BK>(sa + 2 * S::A_TILE);
+                const uint64_t b_lo = umma_desc_k<BK>(sa + 2 * S::A_TILE + BN * BK * 2);
 #pragma unroll
-                for (int k = 0; k < GEMM_BK / 16; ++k) {
+                for (int k = 0; k < BK / 16; ++k) {
                     const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16-byte units
                     umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
                 if (lo_pass) {
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                    for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);
                         umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
                     }
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
+                    for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);
                         umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
                     }
@@ -521,7 +536,7 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-static int make_operand_map(CUtensorMap* map, const psam_operand* op, int box_rows, int box_planes = 1) {
+static int make_operand_map(CUtensorMap* map, const psam_operand* op, int box_rows, int box_planes = 1, int bk = GEMM_BK) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return PSAM_ERR_UNSUPPORTED;
     const int nb1 = op->nb1 > 0 ? op->nb1 : 1, nb2 = op->nb2 > 0 ? op->nb2 : 1;
@@ -533,10 +548,10 @@ static int make_operand_map(CUtensorMap* map, const psam_operand* op, int box_ro
     for (int i = 0; i < 4; ++i)
         if (strides[i] % 16) return PSAM_ERR_ARG;
     if (((uintptr_t)op->hi) % 16) return PSAM_ERR_ARG;
-    cuuint32_t box[5] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows, (cuuint32_t)box_planes, 1, 1};
+    cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)box_rows, (cuuint32_t)box_planes, 1, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(op->hi), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? PSAM_OK : (int)(1000 + r);
 }
@@ -545,11 +560,11 @@ int make_operand_map_ext(CUtensorMap* map, const psam_operand* op, int box_rows,
     return make_operand_map(map, op, box_rows, box_planes);
 }
 
-template <int MAXBN, int STAGES>
+template <int MAXBN, int STAGES, int BK = 64>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbmc, const GemmShape& sh,
                        const GemmEpilogue& ep, cudaStream_t stream) {
-    auto kern = gemm_tc_kernel<MAXBN, STAGES>;
-    using S = GemmSmem<MAXBN, STAGES>;
+    auto kern = gemm_tc_kernel<MAXBN, STAGES, BK>;
+    using S = GemmSmem<MAXBN, STAGES, BK>;
     PSAM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     const int mt = ceil_div(ceil_div(sh.M, GEMM_BM), sh.cm) * sh.cm;  // pad the m-tiles to whole clusters
     cudaLaunchConfig_t cfg = {};
@@ -698,6 +713,20 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     if (rc) return rc;
     rc = make_operand_map(&mbmc, w, bn / cm, 1);
     if (rc) return rc;
+    // wide tiles: BK = 32 (64-byte swizzle) gives 4 half-size stages instead of 2.  MEASURED: 611 vs 618 clouds/s
+    // (config c2, 8 clouds in flight) - no gain, so it is opt-in (PSAM_GEMM_BK32=1).
+    static int bk32 = -1;
+    if (bk32 < 0) {
+        const char* e = getenv("PSAM_GEMM_BK32");
+        bk32 = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (bn > 160 && cm == 1 && bk32) {
+        rc = make_operand_map(&ma, a, GEMM_BM, passes == 3 ? 2 : 1, 32);
+        if (rc) return rc;
+        rc = make_operand_map(&mb, w, bn, passes == 3 ? 2 : 1, 32);
+        if (rc) return rc;
+        return launch_gemm<256, 4, 32>(ma, mb, mb, sh, ep, stream);
+    }
     if (bn <= 64) return launch_gemm<64, 4>(ma, mb, mbmc, sh, ep, stream);
     if (bn <= 128) return launch_gemm<128, 3>(ma, mb, mbmc, sh, ep, stream);
     if (bn <= 160) return launch_gemm<160, 3>(ma, mb, mbmc, sh, ep, stream);

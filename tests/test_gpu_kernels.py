@@ -355,3 +355,40 @@ def test_fused_attention_tc(B, H, L):
     want = (torch.softmax(x[0] @ x[1].transpose(-1, -2) * dh ** -0.5, -1) @ x[2]).transpose(1, 2).reshape(B * L, D).float()
     err = float((att.float() - want).abs().max())
     assert err < 5e-5 * max(1.0, float(want.abs().max())), err
+
+
+@pytest.mark.parametrize("variant", ["bn256_bk32", "bn256_bk64", "two_cta", "cluster4"])
+def test_gemm_tc_variants(variant, monkeypatch):
+    """Opt-in / policy-selected GEMM variants: wide tiles with 64-byte-swizzled half-depth stages (throughput policy),
+    the same with 128-byte swizzle, the 2-CTA cta_group::2 kernel, and W-tile multicast over a 4-CTA cluster."""
+    ops = _ops()
+    env = {"bn256_bk32": {"PSAM_GEMM_BN": "256", "PSAM_GEMM_BK32": "1"}, "bn256_bk64": {"PSAM_GEMM_BN": "256", "PSAM_GEMM_BK32": "0"},
+           "two_cta": {"PSAM_GEMM_2CTA": "1"}, "cluster4": {"PSAM_GEMM_CLUSTER": "4", "PSAM_GEMM_BN": "128"}}[variant]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    if variant == "bn256_bk32" and os.environ.get("PSAM_GEMM_BK32_LATCHED", "") != "1":
+        # the switch is read once per process; run this variant in a fresh interpreter
+        import subprocess
+        import sys
+
+        code = ("import os, sys; os.environ['PSAM_GEMM_BK32_LATCHED'] = '1'; import pytest; "
+                "sys.exit(pytest.main(['-q', '-m', 'gpu', '-p', 'no:cacheprovider', %r + '::test_gemm_tc_variants', '-k', 'bn256_bk32']))" % __file__)
+        env = dict(os.environ, PSAM_GEMM_BK32="1", PSAM_GEMM_BN="256")
+        assert subprocess.call([sys.executable, "-c", code], env=env) == 0
+        return
+    for (M, N, K, sk) in [(512, 3072, 1024, 1), (512, 1024, 2752, 4), (640, 520, 200, 1), (32768, 512, 128, 1)]:
+        a, w, b = _rand(M, K, seed=31), _rand(N, K, seed=32, scale=K ** -0.5), _rand(N, seed=33)
+        A, W = ops.pack_weight(a), ops.pack_weight(w)
+        want = (a.double() @ w.double().t() + b.double())
+        if sk > 1:
+            r = _rand(M, N, seed=34)
+            out = r.clone()
+            ops.gemm(A, W, bias=b, out_f32=out, accumulate=True, split_k=sk)
+            want = (want + r.double())
+        else:
+            out = torch.empty(M, N, device=_dev())
+            osp = ops.Split(M, N, _dev())
+            ops.gemm(A, W, bias=b, out_f32=out, out_split=osp)
+            assert float((osp.float() - out).abs().max()) < 3e-5 * max(1.0, float(want.abs().max()))
+        err = float((out - want.float()).abs().max())
+        assert err < 5e-5 * max(1.0, float(want.abs().max())), (variant, M, N, K, err)
