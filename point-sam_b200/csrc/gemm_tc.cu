@@ -54,6 +54,7 @@ struct GemmShape {
     int passes;  // 1 or 3
     int bn;      // output-tile width actually used (multiple of 32, <= MAXBN)
     int cm;      // cluster size along M (1, 2 or 4): the CTAs of a cluster share the W tile through TMA multicast
+    int prefetch;  // k-blocks of W to prefetch into L2 ahead of the TMA loads (0 = off)
 };
 
 template <int MAXBN, int STAGES, int BK = 64>
@@ -287,6 +288,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // 3-D box (64 x rows x 2 planes) - TMA cost is dominated by a fixed per-operation overhead.
         if (lane < 2) {
             const uint32_t stage_bytes = (lo_pass ? 2u : 1u) * (uint32_t)(S::A_TILE + BN * BK * 2);
+            if (lane == 1 && cm == 1)
+                for (int i = 0; i < shape.prefetch && i < num_kb; ++i) tma_prefetch_l2_5d(&tmap_b, (kb_begin + i) * BK, n_tile * BN, 0, b1, b2);
             for (int i = 0; i < num_kb; ++i) {
                 const int s = i % STAGES;
                 const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
@@ -298,6 +301,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     mbar_arrive_expect_tx(fb, stage_bytes);
                     tma_load_5d(sa, &tmap_a, fb, k0, m_tile * GEMM_BM, 0, b1, b2);
                 } else if (cm == 1) {
+                    // the W tile is read from DRAM exactly once per step: ask L2 for the tile GEMM_PREFETCH k-blocks ahead
+                    if (shape.prefetch > 0 && i + shape.prefetch < num_kb)
+                        tma_prefetch_l2_5d(&tmap_b, (kb_begin + i + shape.prefetch) * BK, n_tile * BN, 0, b1, b2);
                     tma_load_5d(sa + 2 * S::A_TILE, &tmap_b, fb, k0, n_tile * BN, 0, b1, b2);
                 } else {
                     // this CTA fetches rows [crank*BN/cm, (crank+1)*BN/cm) of the W tile once and multicasts them
@@ -661,6 +667,8 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     if ((w->nb1 > 0 ? w->nb1 : 1) != sh.nb1 || (w->nb2 > 0 ? w->nb2 : 1) != sh.nb2) return PSAM_ERR_ARG;
     sh.split_k = split_k;
     sh.passes = passes;
+    sh.prefetch = 0;
+    if (const char* e = getenv("PSAM_GEMM_PREFETCH")) sh.prefetch = atoi(e);
     GemmEpilogue ep;
     ep.out_f32 = o->out_f32, ep.ldo = o->ldo, ep.out_b1 = o->out_b1, ep.out_b2 = o->out_b2;
     ep.out_hi = (__nv_bfloat16*)o->out_hi, ep.out_plane = o->out_plane, ep.ldo_s = o->ldo_s;

@@ -207,6 +207,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void* tmap,
         : "memory");
 }
 
+// L2 prefetch of a tensor tile (no shared-memory destination): hides the DRAM latency of operands that are streamed once
+__device__ __forceinline__ void tma_prefetch_l2_5d(const void* tmap, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
 // multicast variant: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and each of those
 // CTAs' mbarrier (same CTA-relative offset) receives the complete_tx for the bytes written into it
 __device__ __forceinline__ void tma_load_5d_mc(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
