@@ -90,6 +90,10 @@ typedef struct {
     int accumulate;         /* 1: out_f32 += alpha*acc (+bias) with red.add; required when split_k>1 */
     int swiglu;             /* 1: W rows interleaved (gate_i, value_i); out_f32[:, i] = silu(gate_i)*value_i (fp32 out only) */
     int tile_hint;          /* 0: tile width for lowest latency; 1: for lowest SM-time (several clouds in flight); 32..256: explicit */
+    float* gmax;            /* optional fused max-pool: gmax[(row / group_rows) * ld_gmax + col] = max over the group rows
+                               (atomic; caller pre-fills with -inf; group_rows multiple of 32); replaces torch.max(x, dim=-2) */
+    long long ld_gmax;
+    int group_rows;
 } psam_gemm_out;
 
 /* C[M,N] = A[M,K] * W[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators).

@@ -45,6 +45,9 @@ struct GemmEpilogue {
     int act;
     int accumulate;  // 1: out_f32 += result via red.global.add (required for split_k > 1)
     int swiglu;      // 1: columns are (gate, value) pairs; out_f32[:, c/2] = silu(gate) * value
+    float* gmax;     // optional: gmax[(row / group_rows) * ld_gmax + col] = max over the rows of a group (atomic, pre-filled with -inf)
+    long long ld_gmax;
+    int group_rows;  // multiple of 32
 };
 
 struct GemmShape {
@@ -158,6 +161,11 @@ __device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
     return d;
 }
 
+__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
 // Shared epilogue of the 1-CTA and 2-CTA kernels: TMEM -> registers (thread = row) -> per-warp smem transpose ->
 // coalesced global accesses (lane = column: every store/load/red touches one contiguous 128-byte row segment).
 __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const GemmEpilogue& ep, unsigned char* smem_aligned,
@@ -196,6 +204,17 @@ __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const Gemm
             __syncwarp();
             const int col = col0 + lane;
             const bool col_ok = col < shape.N;
+            if (ep.gmax) {
+                // fused max-pool over the rows of a group (torch.max(x, dim=-2) of the mini-PointNet): the 32 rows of
+                // this warp belong to one group; one atomic per column replaces a full write + re-read of x
+                const float bvm = (add_bias && col_ok) ? ep.bias[col] : 0.f;
+                float m = __int_as_float(0xff800000);
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r)
+                    if (row0 + r < shape.M) m = fmaxf(m, fmaf(stg[r * 33 + lane], ep.alpha, bvm));
+                if (col_ok && row0 < shape.M) atomic_max_f32(ep.gmax + (long long)(row0 / ep.group_rows) * ep.ld_gmax + col, m);
+                if (out == nullptr && ohi == nullptr) continue;
+            }
             if (ohi == nullptr) {
                 const float bv = (add_bias && col_ok) ? ep.bias[col] : 0.f;
 #define PSAM_EPI_F32(A, R, C) epi_rows_f32<A, R, C>(stg, lane, row0, shape.M, col, col_ok, ep.alpha, bv, out, res, ep.ldo)
@@ -659,7 +678,7 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     if (passes != 1 && passes != 3) return PSAM_ERR_ARG;
     if (split_k < 1) split_k = 1;
     if (split_k > 1 && !(o->accumulate && o->out_f32 && !o->out_hi && o->act == 0)) return PSAM_ERR_ARG;
-    if (!o->out_f32 && !o->out_hi) return PSAM_ERR_ARG;
+    if (!o->out_f32 && !o->out_hi && !o->gmax) return PSAM_ERR_ARG;
     GemmShape sh;
     sh.M = a->rows, sh.N = w->rows, sh.K = a->k;
     sh.nb1 = a->nb1 > 0 ? a->nb1 : 1;
@@ -675,6 +694,8 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     ep.outs_b1 = o->outs_b1, ep.outs_b2 = o->outs_b2;
     ep.bias = o->bias, ep.resid = o->resid, ep.alpha = o->alpha, ep.act = o->act, ep.accumulate = o->accumulate;
     ep.swiglu = o->swiglu;
+    ep.gmax = o->gmax, ep.ld_gmax = o->ld_gmax, ep.group_rows = o->group_rows;
+    if (ep.gmax && (ep.group_rows <= 0 || ep.group_rows % 32 || ep.accumulate || ep.resid || ep.act || ep.swiglu || sh.nb1 * sh.nb2 != 1)) return PSAM_ERR_ARG;
     if (ep.swiglu && (ep.out_hi || !ep.out_f32 || ep.accumulate || ep.resid || ep.act || (sh.N & 1))) return PSAM_ERR_ARG;
     int bn = choose_bn(sh.M, sh.N, sh.K, sh.nb1 * sh.nb2, sh.split_k, o->tile_hint == 1);
     if (o->tile_hint >= 32 && o->tile_hint <= 256 && o->tile_hint % 32 == 0) bn = o->tile_hint;

@@ -79,11 +79,17 @@ def run_patch_encoder(m, patches: torch.Tensor, want_split: bool = False):
     R, BG = B * L * K, B * L
     h1 = Split(R, pk.h0, dev)
     ops.small_in_linear(patches, pk.w10, pk.b10, pk.g11, pk.be11, pk.eps11, True, ACT_GELU, h1)
-    x1 = torch.empty((R, pk.h0), dtype=torch.float32, device=dev)
     x1s = Split(R, pk.h0, dev)
-    ops.gemm(h1, pk.w13, bias=pk.b13, out_f32=x1, out_split=x1s, passes=PASSES)
     y1s = Split(BG, pk.h0, dev)
-    ops.group_max(x1, BG, K, out_split=y1s)
+    fused_max = K % 32 == 0  # the max-pool over the K rows of a group runs inside the GEMM epilogue
+    if fused_max:
+        y1 = torch.full((BG, pk.h0), float("-inf"), dtype=torch.float32, device=dev)
+        ops.gemm(h1, pk.w13, bias=pk.b13, out_split=x1s, gmax=y1, group_rows=K, passes=PASSES)
+        ops.split_f32(y1, y1s)
+    else:
+        x1 = torch.empty((R, pk.h0), dtype=torch.float32, device=dev)
+        ops.gemm(h1, pk.w13, bias=pk.b13, out_f32=x1, out_split=x1s, passes=PASSES)
+        ops.group_max(x1, BG, K, out_split=y1s)
     # conv2[0] on cat([max, x]) = W_a max + W_b x + b : the pooled half is computed once per group
     t = torch.empty((BG, pk.h1), dtype=torch.float32, device=dev)
     ops.gemm(y1s, pk.w20a, bias=pk.b20, out_f32=t, passes=PASSES)
@@ -91,11 +97,17 @@ def run_patch_encoder(m, patches: torch.Tensor, want_split: bool = False):
     ops.gemm(x1s, pk.w20b, out_f32=x2, passes=PASSES)
     h2 = Split(R, pk.h1, dev)
     ops.layernorm(x2, pk.g21, pk.be21, pk.eps21, gbias=t, group_rows=K, act=ACT_GELU, out_split=h2)
-    x3 = torch.empty((R, pk.cout), dtype=torch.float32, device=dev)
-    ops.gemm(h2, pk.w23, bias=pk.b23, out_f32=x3, passes=PASSES)
-    emb = torch.empty((B, L, pk.cout), dtype=torch.float32, device=dev)
     embs = Split(BG, pk.cout, dev) if want_split else None
-    ops.group_max(x3, BG, K, out_f32=emb, out_split=embs)
+    if fused_max:
+        emb = torch.full((B, L, pk.cout), float("-inf"), dtype=torch.float32, device=dev)
+        ops.gemm(h2, pk.w23, bias=pk.b23, gmax=emb.view(BG, pk.cout), group_rows=K, passes=PASSES)
+        if want_split:
+            ops.split_f32(emb.view(BG, pk.cout), embs)
+    else:
+        x3 = torch.empty((R, pk.cout), dtype=torch.float32, device=dev)
+        ops.gemm(h2, pk.w23, bias=pk.b23, out_f32=x3, passes=PASSES)
+        emb = torch.empty((B, L, pk.cout), dtype=torch.float32, device=dev)
+        ops.group_max(x3, BG, K, out_f32=emb, out_split=embs)
     return (emb, embs) if want_split else emb
 
 
