@@ -48,6 +48,9 @@ struct GemmEpilogue {
     float* gmax;     // optional: gmax[(row / group_rows) * ld_gmax + col] = max over the rows of a group (atomic, pre-filled with -inf)
     long long ld_gmax;
     int group_rows;  // multiple of 32
+    const float* rd_w;   // optional fused row-dot: rd_out[z, c, n] += sum_col act(x[z*rd_rows + n, col]) * rd_w[z, c, col]
+    float* rd_out;       // (pre-zeroed; the hyper-network mask product of the decoder), rd_rows % 32 == 0, rd_c <= 8
+    int rd_rows, rd_c;
 };
 
 struct GemmShape {
@@ -197,6 +200,34 @@ __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const Gemm
             } else {
 #pragma unroll
                 for (int t = 0; t < 32; ++t) v[t] = 0u;
+            }
+            if (ep.rd_out) {
+                // fused "masks = hyper_in @ upscaled^T" (mask_decoder.py:176): thread = row, the activated row chunk is
+                // dotted with the rd_c hyper vectors and accumulated with one atomic per (row, c); the 32768 x 256
+                // upscaled embedding is never written
+                const int row = row0 + lane;
+                const int zz = row0 / ep.rd_rows;
+                const float* wz = ep.rd_w + (long long)zz * ep.rd_c * shape.N;
+                float accd[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) accd[cc] = 0.f;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    const int cidx = col0 + t;
+                    if (cidx < shape.N) {
+                        const float x = apply_act(fmaf(__uint_as_float(v[t]), ep.alpha, add_bias ? ep.bias[cidx] : 0.f), ep.act);
+#pragma unroll
+                        for (int cc = 0; cc < 8; ++cc)
+                            if (cc < ep.rd_c) accd[cc] = fmaf(x, wz[cc * shape.N + cidx], accd[cc]);
+                    }
+                }
+                if (row < shape.M) {
+                    float* o = ep.rd_out + (long long)zz * ep.rd_c * ep.rd_rows + (row - zz * ep.rd_rows);
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc)
+                        if (cc < ep.rd_c) atomicAdd(o + (long long)cc * ep.rd_rows, accd[cc]);
+                }
+                continue;
             }
             __syncwarp();
 #pragma unroll
@@ -678,7 +709,7 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     if (passes != 1 && passes != 3) return PSAM_ERR_ARG;
     if (split_k < 1) split_k = 1;
     if (split_k > 1 && !(o->accumulate && o->out_f32 && !o->out_hi && o->act == 0)) return PSAM_ERR_ARG;
-    if (!o->out_f32 && !o->out_hi && !o->gmax) return PSAM_ERR_ARG;
+    if (!o->out_f32 && !o->out_hi && !o->gmax && !o->rd_out) return PSAM_ERR_ARG;
     GemmShape sh;
     sh.M = a->rows, sh.N = w->rows, sh.K = a->k;
     sh.nb1 = a->nb1 > 0 ? a->nb1 : 1;
@@ -695,6 +726,9 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     ep.bias = o->bias, ep.resid = o->resid, ep.alpha = o->alpha, ep.act = o->act, ep.accumulate = o->accumulate;
     ep.swiglu = o->swiglu;
     ep.gmax = o->gmax, ep.ld_gmax = o->ld_gmax, ep.group_rows = o->group_rows;
+    ep.rd_w = o->rd_w, ep.rd_out = o->rd_out, ep.rd_rows = o->rd_rows, ep.rd_c = o->rd_c;
+    if (ep.rd_out && (!ep.rd_w || ep.rd_rows <= 0 || ep.rd_rows % 32 || ep.rd_c <= 0 || ep.rd_c > 8 || ep.accumulate || ep.resid || ep.swiglu ||
+                      ep.gmax || ep.out_f32 || ep.out_hi || split_k != 1 || sh.nb1 * sh.nb2 != 1)) return PSAM_ERR_ARG;
     if (ep.gmax && (ep.group_rows <= 0 || ep.group_rows % 32 || ep.accumulate || ep.resid || ep.act || ep.swiglu || sh.nb1 * sh.nb2 != 1)) return PSAM_ERR_ARG;
     if (ep.swiglu && (ep.out_hi || !ep.out_f32 || ep.accumulate || ep.resid || ep.act || (sh.N & 1))) return PSAM_ERR_ARG;
     int bn = choose_bn(sh.M, sh.N, sh.K, sh.nb1 * sh.nb2, sh.split_k, o->tile_hint == 1);

@@ -7,6 +7,7 @@ lazily and cached per module; the cache is keyed on parameter storage/version so
 """
 from __future__ import annotations
 
+import os
 import math
 from ctypes import byref
 from typing import Optional
@@ -18,6 +19,7 @@ from . import ops
 from .ops import ACT_GELU, ACT_NONE, ACT_RELU, Split
 
 FUSED_ATTENTION = True
+FUSED_MASK_DOT = os.environ.get("PSAM_FUSED_MASK_DOT", "1") != "0"
 PASSES = 3  # split-bf16 (fp32-parity) mode; 1 = plain bf16 (fails the 1e-3 parity bound)
 
 
@@ -443,9 +445,6 @@ def run_mask_decoder(md, pc_embeddings, pc_pe, sparse, dense, aux, multimask_out
     nv.check(nv.lib().psam_interp_ln_gelu(nv.ptr(f0), Z, rep, G, D, nv.ptr(aux.interp_index), nv.ptr(aux.interp_weight), N,
                                           nv.ptr(pk.up1[0]), nv.ptr(pk.up1[1]), pk.up1[2], u1.ptr(), u1.plane, u1.pitch,
                                           nv.stream()), "interp_ln_gelu")
-    u2 = torch.empty((Z * N, D), dtype=torch.float32, device=dev)
-    ops.gemm(u1, pk.up3w, bias=pk.up3b, out_f32=u2, act=ACT_GELU, passes=PASSES)
-
     # hyper-network MLPs on the selected mask tokens (mask_decoder.py:167-175), batched over tokens
     i0 = ids[0]
     x = hs
@@ -457,8 +456,15 @@ def run_mask_decoder(md, pc_embeddings, pc_pe, sparse, dense, aux, multimask_out
         ops.linear_f32(x, w[i0:i0 + C], b[i0:i0 + C], act=ACT_RELU if li < 2 else ACT_NONE, out=y, M=Z, K=D, ldx=ld, Z=C,
                        x_z=D, w_z=D * D, b_z=D, y_z=D, ldy=C * D, x_off=xoff)
         x, ld, xoff, hyper = y, C * D, 0, y
-    masks = torch.empty((Z, C, N), dtype=torch.float32, device=dev)
-    nv.check(nv.lib().psam_mask_dot(nv.ptr(u2), D, nv.ptr(hyper), Z, C, N, D, nv.ptr(masks), nv.stream()), "mask_dot")
+    if FUSED_MASK_DOT and N % 32 == 0 and C <= 8:
+        # output_upscaling[3..4] (Linear + GELU) and the hyper-network product fused into one GEMM epilogue
+        masks = torch.zeros((Z, C, N), dtype=torch.float32, device=dev)
+        ops.gemm(u1, pk.up3w, bias=pk.up3b, act=ACT_GELU, passes=PASSES, rowdot=(hyper, masks))
+    else:
+        u2 = torch.empty((Z * N, D), dtype=torch.float32, device=dev)
+        ops.gemm(u1, pk.up3w, bias=pk.up3b, out_f32=u2, act=ACT_GELU, passes=PASSES)
+        masks = torch.empty((Z, C, N), dtype=torch.float32, device=dev)
+        nv.check(nv.lib().psam_mask_dot(nv.ptr(u2), D, nv.ptr(hyper), Z, C, N, D, nv.ptr(masks), nv.stream()), "mask_dot")
 
     # IoU head on the iou token (mask_decoder.py:180-182)
     y = hs

@@ -111,7 +111,7 @@ def gemm_raw(a: Operand, w: Operand, out: GemmOut, passes: int = 3, split_k: int
 def gemm(a: Split, w: Split, *, bias=None, out_f32: Optional[torch.Tensor] = None, out_split: Optional[Split] = None,
          resid: Optional[torch.Tensor] = None, act: int = ACT_NONE, alpha: float = 1.0, accumulate: bool = False,
          split_k: int = 1, passes: int = 3, rows: Optional[int] = None, swiglu: bool = False,
-         gmax: Optional[torch.Tensor] = None, group_rows: int = 0):
+         gmax: Optional[torch.Tensor] = None, group_rows: int = 0, rowdot=None):
     """out = act(alpha * a @ w^T + bias (+ resid)); a [M,K], w [N,K] split-bf16."""
     M = rows if rows is not None else a.rows
     o = GemmOut()
@@ -128,6 +128,9 @@ def gemm(a: Split, w: Split, *, bias=None, out_f32: Optional[torch.Tensor] = Non
     o.swiglu = int(swiglu)
     if gmax is not None:
         o.gmax, o.ld_gmax, o.group_rows = nv.ptr(gmax), gmax.shape[-1], group_rows
+    if rowdot is not None:  # (w [Z,C,N], out [Z,C,rows] zero-filled)
+        rw, ro = rowdot
+        o.rd_w, o.rd_out, o.rd_rows, o.rd_c = nv.ptr(rw), nv.ptr(ro), ro.shape[-1], ro.shape[-2]
     gemm_raw(a.operand(rows=M), w.operand(), o, passes, split_k)
 
 
