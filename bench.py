@@ -112,6 +112,44 @@ def cpu_reference_throughput(cfg, steps: int, warmup: int):
     return steps * bpg / tot, tot / steps * 1e3, torch.get_num_threads()
 
 
+def gpu_reference_throughput(cfg, steps: int, warmup: int):
+    """SURVEY.md 8(d) "GPU reference beside it": the reference's own GPU execution model on this box - its FPS kernel
+    compiled for sm_100a (oracle/_ref, when it travelled) + cdist/topk + PyTorch fp32 eager modules (the oracle
+    restatement moved to cuda:0).  A reported comparison point only (like cpu_baseline); nothing here is product code."""
+    from oracle import build_ref, synth, torch_ref
+
+    enc, N, G, K, bpg, P, kind = cfg
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ref = build_ref.load_ref()
+    saved = torch_ref.sample_farthest_points
+    if ref is not None:
+        torch_ref.sample_farthest_points = lambda pts, g: ref.sample_farthest_points_cuda(pts.float().contiguous(), g)
+    out = {"fps": "reference kernel (oracle/_ref)" if ref is not None else "oracle C port on the host (oracle/_ref absent)",
+           "kind": "reference execution model: torkit3d FPS + cdist/topk + PyTorch eager modules, same GPU", "steps": steps}
+    try:
+        model = torch_ref.build_model(enc, G, K, seed=1234).to(dev)
+        clouds = [tuple(t.to(dev) for t in synth.make_batch(bpg, N, 0 + 17 * i, kind)) for i in range(2)]
+        prompts = [tuple(t.to(dev) for t in synth.make_prompts(c[0].cpu(), P, i)) for i, c in enumerate(clouds)]
+        for tag, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                for i in range(warmup):
+                    model.predict_masks(*clouds[i % 2], *prompts[i % 2], None, True)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(steps):
+                    model.predict_masks(*clouds[i % 2], *prompts[i % 2], None, True)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[tag] = {"value": bpg / ms * 1e3, "unit": "clouds/s", "ms_per_step": ms}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch_ref.sample_farthest_points = saved
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -226,6 +264,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--depth", type=int, default=8, help="clouds in flight per GPU (independent streams/graphs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the same-GPU PyTorch-eager reference timing")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -416,6 +455,11 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "clouds/s", "cores": cores, "kind": "port",
                                     "sample": "3 clouds of the same workload after 1 warm-up; oracle port "
                                               "(C restatement of the FPS kernel + PyTorch fp32 CPU path, all host threads)"}
+        if world == 1 and not args.no_gpu_reference:
+            try:
+                line["gpu_reference"] = gpu_reference_throughput(cfg, 10, 3)
+            except Exception as e:  # a comparison figure must never break the bench line
+                line["gpu_reference"] = {"unavailable": repr(e)[:160]}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -89,12 +89,58 @@ CASES = [
 ]
 
 
+def sampler_cases():
+    """Inputs for the prompt-sampler fixture: (points [B,N,3], gt [B,M,N] bool, list of pred_logits [B*M,N] | None)."""
+    B, M, N = 2, 3, 1500
+    xyz, _ = synth.make_batch(B, N, 40, "ball")
+    g = torch.Generator().manual_seed(41)
+    gt = torch.stack([torch.stack([xyz[b, :, m % 3] > (-0.2 + 0.25 * m) for m in range(M)]) for b in range(B)])
+    sign = gt.reshape(B * M, N).float() * 2 - 1
+    noisy = sign * (torch.rand(B * M, N, generator=g) * 2 - 0.35)          # ~17% of the points flip
+    only_fn = torch.where(gt.reshape(B * M, N) & (torch.rand(B * M, N, generator=g) < 0.2), -torch.ones(1), sign)
+    only_fp = torch.where(~gt.reshape(B * M, N) & (torch.rand(B * M, N, generator=g) < 0.2), torch.ones(1), sign)
+    mixed = noisy.clone()
+    mixed[0] = sign[0]              # perfect prediction for one mask -> ground-truth fallback (common.py:420-428)
+    mixed[1] = only_fn[1]
+    mixed[2] = only_fp[2]
+    return xyz, gt, [None, noisy, only_fn, only_fp, sign, mixed]
+
+
+@torch.no_grad()
+def sampler_fixture(ref, out_dir):
+    """sample_prompts_adapter of the reference (pc_sam/model/common.py:287-318) with the CUDA-only chamfer wrapper
+    replaced by the oracle's exact nearest-neighbour (same arithmetic as chamfer_distance_kernel.cu:62-76)."""
+    common = ref["common"]
+
+    def fake_chamfer(xyz1, xyz2, **kw):
+        _, d12 = tokenizer_ref.knn(xyz1.numpy(), xyz2.numpy(), 1)
+        _, d21 = tokenizer_ref.knn(xyz2.numpy(), xyz1.numpy(), 1)
+        return torch.from_numpy(d12[..., 0]), torch.from_numpy(d21[..., 0])
+
+    common.chamfer_distance = fake_chamfer
+    xyz, gt, preds = sampler_cases()
+    pack = dict(xyz=xyz.numpy(), gt=gt.numpy(), n=len(preds))
+    for i, pr in enumerate(preds):
+        c, l = common.sample_prompts_adapter(xyz, gt, pr, is_eval=True)
+        oc, ol = torch_ref.sample_prompts_eval(xyz, gt, pr)
+        assert torch.equal(c, oc) and torch.equal(l, ol), f"oracle sampler differs from the reference in case {i}"
+        if pr is not None:
+            pack[f"pred{i}"] = pr.numpy()
+        pack[f"coords{i}"] = c.numpy()
+        pack[f"labels{i}"] = l.numpy()
+    np.savez_compressed(os.path.join(out_dir, "prompt_sampler.npz"), **pack)
+    print("prompt sampler fixture written:", [tuple(pack[f"coords{i}"].shape) for i in range(len(preds))])
+
+
 @torch.no_grad()
 def main():
     torch.set_num_threads(8)
     ref = import_reference()
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    sampler_fixture(ref, out_dir)
+    if "--only-sampler" in sys.argv:
+        return
     for name, B, N, G, K, encoder, P, kind, seed in CASES:
         xyz, feats = synth.make_batch(B, N, seed, kind)
         pc, pl = synth.make_prompts(xyz, P, seed)

@@ -584,6 +584,56 @@ class PointCloudSAM(nn.Module):
         return outs
 
 
+
+# ---------------------------------------------------------------------------------------------------------
+# ground-truth prompt sampling (pc_sam/model/common.py:371-474), evaluation branch of sample_prompts_adapter
+# ---------------------------------------------------------------------------------------------------------
+def _farthest_from_border(coords, labels, gt):
+    """common.py:445-474: among points with label 1, the one whose nearest label-0 point is farthest (squared distance
+    with the chamfer kernel's arithmetic, chamfer_distance_kernel.cu:62-76; first index on ties like torch.argmax)."""
+    bg, fg = labels == 0, labels == 1
+    if int(bg.sum()) == 0 or int(fg.sum()) == 0:
+        return None, None, -1
+    q = coords[fg].detach().cpu().float().numpy()[None]
+    k = coords[bg].detach().cpu().float().numpy()[None]
+    _, d2 = tokenizer_ref.knn(q, k, 1)
+    d = torch.from_numpy(d2[0, :, 0])
+    i = torch.argmax(d)
+    return coords[fg][i][None], gt[fg][i][None], float(d.max())
+
+
+def sample_fixed_points(points, gt_masks, pred_logits, threshold=None, from_error_region=False):
+    """common.py:371-442.  points [B,N,3], gt_masks [B,M,N] bool, pred_logits [B*M,N] | None."""
+    B, M, _ = gt_masks.shape
+    if pred_logits is None:
+        fn, fp = gt_masks, torch.zeros_like(gt_masks)
+    else:
+        pl = pred_logits.reshape(B, M, -1)
+        pm = pl > 0 if threshold is None else pl.sigmoid() > threshold
+        fn, fp = gt_masks & ~pm, ~gt_masks & pm
+    pts, labs = [], []
+    for b in range(B):
+        for m in range(M):
+            if from_error_region:
+                c, l, _ = _farthest_from_border(points[b], (fn | fp)[b, m], gt_masks[b, m])
+            else:
+                c, l, pd = _farthest_from_border(points[b], fn[b, m], gt_masks[b, m])
+                c2, l2, nd = _farthest_from_border(points[b], fp[b, m], gt_masks[b, m])
+                if not pd > nd:
+                    if nd == -1:
+                        c, l, _ = _farthest_from_border(points[b], gt_masks[b, m], gt_masks[b, m])
+                    else:
+                        c, l = c2, l2
+            pts.append(c)
+            labs.append(l)
+    return torch.stack(pts), torch.stack(labs)
+
+
+def sample_prompts_eval(points, gt_masks, pred_logits, threshold=None):
+    """sample_prompts_adapter(..., is_eval=True) (common.py:287-318)."""
+    return sample_fixed_points(points, gt_masks, pred_logits, threshold, from_error_region=pred_logits is None)
+
+
 def build_model(encoder: str = "eva02_large_patch14_448", num_patches=512, patch_size=64, embed_dim=256,
                 prompt_iters=5, seed: Optional[int] = 1234) -> PointCloudSAM:
     """Mirror of configs/model/{base,default,giant}.yaml with default torch initialisation."""

@@ -326,6 +326,137 @@ nn_distance_kernel(const float* __restrict__ q, const float* __restrict__ key, i
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Batched ground-truth prompt sampler (pc_sam/model/common.py:371-474, the body of forward(is_eval=True) between two
+// decoder passes).  The reference loops over (cloud, mask) in Python, compacts foreground / background points with
+// boolean indexing, calls the chamfer kernel and compares results on the host (several synchronisations per mask).
+// Here one launch handles every (cloud, mask, region): region membership is evaluated on the fly from the ground truth
+// and the logits, the nearest-background distance of every foreground point is computed with the chamfer kernel's
+// arithmetic (fma(dz,dz,fma(dy,dy,dx*dx)), d = background - foreground), and the farthest foreground point is kept by
+// a 64-bit atomic max on (distance bits, ~index): ties resolve to the lowest index exactly like torch.argmax over the
+// compacted array.  A second tiny kernel applies the reference's selection rules.  No host round trip.
+//   region 0: false negatives  gt & ~pred      (mode 0, "error region" sampling: (gt & ~pred) | (~gt & pred))
+//   region 1: false positives ~gt &  pred
+//   region 2: the ground-truth mask itself (fallback when both error regions are empty)
+__device__ __forceinline__ int border_region_label(int region, int mode, bool gt, bool pred) {
+    if (mode == 0) return (gt != pred) ? 1 : 0;
+    if (region == 0) return (gt && !pred) ? 1 : 0;
+    if (region == 1) return (!gt && pred) ? 1 : 0;
+    return gt ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+border_farthest_kernel(const float* __restrict__ coords, const unsigned char* __restrict__ gt, const float* __restrict__ logits,
+                       const unsigned char* __restrict__ pred_mask, int M, int N, int mode,
+                       unsigned long long* __restrict__ best /* [BM][3] */) {
+    __shared__ float s_k[256 * 3];
+    __shared__ unsigned char s_lab[256];
+    __shared__ unsigned long long s_best[8];
+    const int bm = blockIdx.z, region = blockIdx.y;
+    const float* xyz = coords + (size_t)(bm / M) * N * 3;
+    const unsigned char* g = gt + (size_t)bm * N;
+    const float* lg = logits ? logits + (size_t)bm * N : nullptr;
+    const unsigned char* pmk = pred_mask ? pred_mask + (size_t)bm * N : nullptr;
+    auto label_of = [&](int j) {
+        const bool p = lg ? (lg[j] > 0.f) : (pmk ? pmk[j] != 0 : false);
+        return border_region_label(region, mode, g[j] != 0, p);
+    };
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    float x = 0.f, y = 0.f, z = 0.f;
+    int mine = 0;
+    if (i < N) {
+        x = xyz[(size_t)i * 3], y = xyz[(size_t)i * 3 + 1], z = xyz[(size_t)i * 3 + 2];
+        mine = label_of(i);
+    }
+    if (!__syncthreads_or(mine)) return;  // no foreground point in this block
+    float bestd = 3.4e38f;
+    bool any_bg = false;
+    for (int j0 = 0; j0 < N; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        if (j < N) {
+            s_k[threadIdx.x * 3] = xyz[(size_t)j * 3];
+            s_k[threadIdx.x * 3 + 1] = xyz[(size_t)j * 3 + 1];
+            s_k[threadIdx.x * 3 + 2] = xyz[(size_t)j * 3 + 2];
+            s_lab[threadIdx.x] = (unsigned char)label_of(j);
+        }
+        __syncthreads();
+        const int lim = min(256, N - j0);
+        for (int t = 0; t < lim; ++t) {
+            if (s_lab[t] == 0) {  // uniform across the block: no divergence
+                any_bg = true;
+                bestd = fminf(bestd, sqdist3(s_k[t * 3], s_k[t * 3 + 1], s_k[t * 3 + 2], x, y, z));
+            }
+        }
+        __syncthreads();
+    }
+    unsigned long long key = 0ull;
+    if (mine && any_bg) key = ((unsigned long long)__float_as_uint(bestd) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other > key ? other : key;
+    }
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) key = s_best[w] > key ? s_best[w] : key;
+        if (key) atomicMax(best + (size_t)bm * 3 + region, key);
+    }
+}
+
+__global__ void border_select_kernel(const float* __restrict__ coords, const unsigned char* __restrict__ gt,
+                                     const unsigned long long* __restrict__ best, int BM, int M, int N, int mode,
+                                     float* __restrict__ out_xyz, unsigned char* __restrict__ out_label, int* __restrict__ status) {
+    const int bm = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bm >= BM) return;
+    const unsigned long long p = best[(size_t)bm * 3], n = best[(size_t)bm * 3 + 1], g = best[(size_t)bm * 3 + 2];
+    const float pd = p ? __uint_as_float((unsigned)(p >> 32)) : -1.f;
+    const float nd = n ? __uint_as_float((unsigned)(n >> 32)) : -1.f;
+    unsigned long long pick;
+    if (mode == 0) pick = p;                  // from_error_region: the single merged region
+    else if (pd > nd) pick = p;               // common.py:417-419
+    else if (nd == -1.f) pick = g;            // :420-428 both error regions empty -> sample inside the ground truth
+    else pick = n;                            // :429-431
+    if (!pick) {  // the reference fails here (torch.stack of None); reported through status
+        out_xyz[bm * 3] = out_xyz[bm * 3 + 1] = out_xyz[bm * 3 + 2] = 0.f;
+        out_label[bm] = 0;
+        atomicExch(status, 1);
+        return;
+    }
+    const unsigned idx = 0xFFFFFFFFu - (unsigned)(pick & 0xFFFFFFFFull);
+    const float* xyz = coords + ((size_t)(bm / M) * N + idx) * 3;
+    out_xyz[bm * 3] = xyz[0], out_xyz[bm * 3 + 1] = xyz[1], out_xyz[bm * 3 + 2] = xyz[2];
+    out_label[bm] = gt[(size_t)bm * N + idx];
+}
+
+}  // namespace psam
+
+extern "C" size_t psam_border_prompt_workspace_bytes(int B, int M) { return (size_t)B * M * 3 * sizeof(unsigned long long); }
+
+extern "C" int psam_border_prompt_f32(const float* coords, const unsigned char* gt_masks, const float* pred_logits,
+                                      const unsigned char* pred_masks, int B, int M, int N, int from_error_region,
+                                      float* prompt_xyz_out, unsigned char* prompt_label_out, int* status, void* workspace,
+                                      cudaStream_t stream) {
+    using namespace psam;
+    if (!coords || !gt_masks || !prompt_xyz_out || !prompt_label_out || !status || !workspace || B <= 0 || M <= 0 || N <= 0 ||
+        (pred_logits && pred_masks))
+        return PSAM_ERR_ARG;
+    if ((long long)B * M > 65535) return PSAM_ERR_UNSUPPORTED;
+    const int BM = B * M;
+    const int mode = from_error_region ? 0 : 1;
+    unsigned long long* best = static_cast<unsigned long long*>(workspace);
+    PSAM_CUDA_TRY(cudaMemsetAsync(best, 0, psam_border_prompt_workspace_bytes(B, M), stream));
+    border_farthest_kernel<<<dim3(ceil_div(N, 256), mode == 0 ? 1 : 3, BM), 256, 0, stream>>>(coords, gt_masks, pred_logits, pred_masks, M, N,
+                                                                                            mode, best);
+    PSAM_LAUNCH_CHECK();
+    border_select_kernel<<<ceil_div(BM, 128), 128, 0, stream>>>(coords, gt_masks, best, BM, M, N, mode, prompt_xyz_out, prompt_label_out,
+                                                                status);
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+namespace psam {
 }  // namespace psam
 
 extern "C" int psam_nn_distance_f32(const float* query, const float* key, int n1, int n2, float* dist_out,

@@ -28,6 +28,7 @@ class PointCloudSAM(nn.Module):
         self.prompt_iters = prompt_iters
         self.enable_mask_refinement_iterations = enable_mask_refinement_iterations
         self._cloud = None  # cache filled by set_pointcloud
+        self._cloud_key = None
 
     # ------------------------------------------------------------------------------------------
     def _encode(self, coords, features):
@@ -51,8 +52,14 @@ class PointCloudSAM(nn.Module):
     # ------------------------------------------------------------------------------------------
     def set_pointcloud(self, xyz: torch.Tensor, rgb: torch.Tensor):
         """demo/app.py:199 - encode once, keep the embeddings for subsequent prompt decodes."""
+        key = (xyz.data_ptr(), xyz._version, tuple(xyz.shape), rgb.data_ptr(), rgb._version,
+               self.pc_encoder.patch_embed.grouper.num_groups, self.pc_encoder.patch_embed.grouper.group_size)
+        if self._cloud is not None and self._cloud_key == key:
+            return  # same tensors, unmodified: keep the embeddings (the demo calls this on every click)
         with torch.no_grad():
             self._cloud = self._encode(xyz.float().contiguous(), rgb.float().contiguous())
+        self._cloud_key = key
+        self._cloud_keepalive = (xyz, rgb)  # the key holds data_ptr()s: keep the storages alive so they cannot be recycled
 
     def predict_masks(self, *args, **kwargs):
         """Two call forms:

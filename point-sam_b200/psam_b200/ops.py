@@ -99,6 +99,27 @@ def nn_distance(query: torch.Tensor, key: torch.Tensor):
     return d
 
 
+def border_prompt(coords: torch.Tensor, gt_masks: torch.Tensor, pred_logits: Optional[torch.Tensor] = None,
+                  pred_masks: Optional[torch.Tensor] = None, from_error_region: bool = False):
+    """Batched farthest-from-border prompt sampling (psam_border_prompt_f32).  coords [B,N,3], gt_masks [B,M,N] bool,
+    prediction as logits [B*M,N] or bool masks [B*M,N] or neither.  Returns (xyz [B*M,1,3], labels [B*M,1] bool, status)."""
+    B, M, N = gt_masks.shape
+    c = coords.float().contiguous()
+    g = gt_masks.contiguous().view(torch.uint8) if gt_masks.dtype == torch.bool else gt_masks.to(torch.uint8).contiguous()
+    lg = pred_logits.float().contiguous() if pred_logits is not None else None
+    pm = None
+    if pred_masks is not None:
+        pm = pred_masks.contiguous().view(torch.uint8) if pred_masks.dtype == torch.bool else pred_masks.to(torch.uint8).contiguous()
+    dev = c.device
+    xyz = torch.empty((B * M, 1, 3), dtype=torch.float32, device=dev)
+    lab = torch.empty((B * M, 1), dtype=torch.uint8, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(nv.lib().psam_border_prompt_workspace_bytes(B, M), dtype=torch.uint8, device=dev)
+    nv.check(nv.lib().psam_border_prompt_f32(nv.ptr(c), nv.ptr(g), nv.ptr(lg), nv.ptr(pm), B, M, N, int(from_error_region), nv.ptr(xyz),
+                                             nv.ptr(lab), nv.ptr(status), nv.ptr(ws), nv.stream()), "border_prompt")
+    return xyz, lab.view(torch.bool), status
+
+
 GEMM_TILE_HINT = 0  # 0 = latency-optimal tiles, 1 = SM-time-optimal tiles (set by PipelinedPredictor)
 
 

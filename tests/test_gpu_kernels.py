@@ -203,6 +203,41 @@ def test_gemm_tc_epilogues_and_splitk():
     assert float((o - (0.125 * (base - b.double())).float()).abs().max()) < 1e-4
 
 
+def test_gemm_tc_fused_group_max_and_row_dot():
+    """Epilogue fusions of the tokenizer / decoder: max over the rows of a group (common.py:497 torch.max(x, dim=-2))
+    and the hyper-network product masks = hyper @ gelu(linear(u))^T (mask_decoder.py:176)."""
+    ops = _ops()
+    # --- group max, with and without the split copy of the un-pooled rows ---
+    for (G, Kg, N, K) in [(24, 64, 128, 128), (7, 32, 512, 256), (5, 96, 200, 64)]:
+        M = G * Kg
+        a, w, b = _rand(M, K, seed=11), _rand(N, K, seed=12, scale=K ** -0.5), _rand(N, seed=13)
+        A, W = ops.pack_weight(a), ops.pack_weight(w)
+        full = (a.double() @ w.double().t() + b.double()).float()
+        want = full.view(G, Kg, N).max(dim=1).values
+        y = torch.full((G, N), float("-inf"), device=_dev())
+        ops.gemm(A, W, bias=b, gmax=y, group_rows=Kg)
+        assert float((y - want).abs().max()) < 1e-4
+        y2 = torch.full((G, N), float("-inf"), device=_dev())
+        xs = ops.Split(M, N, _dev())
+        ops.gemm(A, W, bias=b, out_split=xs, gmax=y2, group_rows=Kg)
+        assert torch.equal(y, y2)
+        assert float((xs.float() - full).abs().max()) < 1e-4
+    # --- row dot: Z batches of rd_rows rows, C hyper vectors each ---
+    for (Z, R, C, N, K) in [(2, 4096, 4, 256, 256), (3, 160, 1, 256, 256), (1, 2048, 3, 96, 128)]:
+        M = Z * R
+        a, w, b = _rand(M, K, seed=21), _rand(N, K, seed=22, scale=K ** -0.5), _rand(N, seed=23)
+        hyper = _rand(Z, C, N, seed=24)
+        A, W = ops.pack_weight(a), ops.pack_weight(w)
+        u = torch.nn.functional.gelu((a.double() @ w.double().t() + b.double())).view(Z, R, N)
+        want = (hyper.double() @ u.transpose(1, 2)).float()
+        masks = torch.zeros(Z, C, R, device=_dev())
+        ops.gemm(A, W, bias=b, act=ops.ACT_GELU, rowdot=(hyper, masks))
+        assert float((masks - want).abs().max()) < 2e-4 * max(1.0, float(want.abs().max()))
+    # invalid combinations are refused, not silently mis-computed
+    with pytest.raises(RuntimeError):
+        ops.gemm(A, W, bias=b, rowdot=(hyper, torch.zeros(Z, C, R + 1, device=_dev())))  # rows not a multiple of 32
+
+
 def test_gemm_tc_batched_attention_shapes():
     """The batched operand views used by the ViT attention (heads = b1, clouds = b2)."""
     from psam_b200 import native as nv

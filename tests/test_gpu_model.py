@@ -176,3 +176,131 @@ def test_graph_and_pipelined_predictors_match_eager():
         m, i = pp.result(t, to_host=True)
         torch.testing.assert_close(m, want[t][0], atol=2e-5, rtol=1e-4)
         torch.testing.assert_close(i, want[t][1], atol=2e-5, rtol=1e-4)
+
+
+def test_batched_prompt_sampler_vs_reference_fixture_and_oracle(golden_dir):
+    """the batched border sampler against the reference's own outputs (fixture) and against the
+    oracle on larger seeded inputs, including the empty-region fallbacks."""
+    from pc_sam.model import prompt_sampling as ps
+    from psam_b200 import ops
+
+    d = torch.device("cuda:0")
+    z = np.load(os.path.join(golden_dir, "prompt_sampler.npz"))
+    xyz, gt = torch.from_numpy(z["xyz"]), torch.from_numpy(z["gt"])
+    for i in range(int(z["n"])):
+        pred = torch.from_numpy(z[f"pred{i}"]) if f"pred{i}" in z else None
+        c, l = ps.sample_prompts_adapter(xyz.to(d), gt.to(d), pred.to(d) if pred is not None else None, is_eval=True)
+        assert c.shape == (6, 1, 3) and l.shape == (6, 1) and l.dtype == torch.bool
+        assert np.array_equal(c.cpu().numpy(), z[f"coords{i}"]), i
+        assert np.array_equal(l.cpu().numpy(), z[f"labels{i}"]), i
+    # larger seeded case vs the oracle; thresholded prediction goes through the mask input of the kernel
+    B, M, N = 2, 2, 6000
+    xyz, _ = synth.make_batch(B, N, 77, "kitti")
+    g = torch.Generator().manual_seed(78)
+    gt = torch.stack([torch.stack([(xyz[b] - xyz[b, 100 * (m + 1)]).norm(dim=-1) < 0.5 + 0.1 * m for m in range(M)]) for b in range(B)])
+    pred = (gt.reshape(B * M, N).float() * 2 - 1) * (torch.rand(B * M, N, generator=g) * 2 - 0.5)
+    for thr in (None, 0.6):
+        want_c, want_l = torch_ref.sample_fixed_points(xyz, gt, pred, thr, False)
+        c, l = ps.sample_fixed_points(xyz.to(d), gt.to(d), pred.to(d), thr, False)
+        assert torch.equal(c.cpu(), want_c) and torch.equal(l.cpu(), want_l), thr
+    want_c, want_l = torch_ref.sample_fixed_points(xyz, gt, pred, None, True)
+    c, l = ps.sample_fixed_points(xyz.to(d), gt.to(d), pred.to(d), None, True)
+    assert torch.equal(c.cpu(), want_c) and torch.equal(l.cpu(), want_l)
+    # single-mask form and the batched kernel agree
+    c1, l1, _ = ps.sample_furthest_points_from_border(xyz[0].to(d), gt[0, 0].to(d).long(), gt[0, 0].to(d))
+    c0, l0 = ps.sample_prompts_adapter(xyz[:1].to(d), gt[:1, :1].to(d), None, is_eval=True)
+    assert torch.equal(c1, c0[0]) and bool(l1[0]) == bool(l0[0, 0])
+    # a mask without border (empty / full) is an error, as in the reference (torch.stack of None)
+    bad = gt.clone()
+    bad[1, 0] = True
+    with pytest.raises(RuntimeError):
+        ps.sample_prompts_adapter(xyz.to(d), bad.to(d), None, is_eval=True)
+    _, _, st = ops.border_prompt(xyz.to(d), gt.to(d))
+    assert int(st.item()) == 0
+
+
+def test_eval_driver_and_demo_session(tmp_path):
+    """the evaluation caller (binary PLY -> forward(is_eval=True) -> IoU) and the demo wire
+    format (ASCII PLY, /segment JSON) on top of the CUDA path, checked against the oracle."""
+    import sys
+
+    from pc_sam.model.loss import compute_iou
+    from pc_sam.utils import ply
+    from psam_b200 import native as nv
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "point-sam_b200"))
+    from demo.app import SegmentSession
+    from evaluation import eval_kitti
+
+    model, oracle = _build("eva02_test_tiny", 32, 16, 9)
+    d = torch.device("cuda:0")
+    # ---- evaluation driver ----
+    files = []
+    for i, n in enumerate((700, 300)):
+        xyz, feats = synth.make_batch(1, n, 50 + i, "kitti")
+        raw = xyz[0].numpy() * 7.5 + np.array([3.0, -2.0, 1.0], dtype=np.float32)
+        rgb = ((feats[0].numpy() * 0.5 + 0.5) * 255).astype(np.uint8)
+        label = (xyz[0, :, 0] > 0.05).numpy().astype(np.int32)
+        f = str(tmp_path / f"car_{i:04d}.ply")
+        ply.write_ply(f, {"x": raw[:, 0].copy(), "y": raw[:, 1].copy(), "z": raw[:, 2].copy(), "R": rgb[:, 0].copy(),
+                          "G": rgb[:, 1].copy(), "B": rgb[:, 2].copy(), "label": label})
+        files.append(f)
+    model.prompt_iters = oracle.prompt_iters = 3
+    res = eval_kitti.evaluate(model, files, log=None)
+    assert res["total"].shape == (3,) and list(res["per_object"]) == ["car"] and np.allclose(res["object_mean"], res["total"])
+    # replay the first crop: same prompts through the oracle give the same masks, hence the same IoU
+    data = eval_kitti.transform_fn(eval_kitti.load_crop(files[0]), device=d)
+    eval_kitti.set_group_shape(model, 700)
+    outs = model(**data, is_eval=True)
+    g = oracle.pc_encoder.patch_embed.grouper
+    g.num_groups, g.group_size = 700, 256
+    pcs = [outs[0]["prompt_coords"].cpu()] + [outs[t]["prompt_coords"][:, t:t + 1].cpu() for t in (1, 2)]
+    pls = [outs[0]["prompt_labels"].cpu()] + [outs[t]["prompt_labels"][:, t:t + 1].cpu() for t in (1, 2)]
+    with torch.no_grad():
+        want = oracle.predict_iterative(data["coords"].cpu(), data["features"].cpu(), pcs, pls)
+    for t in range(3):
+        np.testing.assert_allclose(outs[t]["masks"].cpu().numpy(), want[t]["masks"].numpy(), atol=ATOL, rtol=RTOL)
+    # the sampled prompts are those the reference sampler picks from the oracle's own masks
+    gt = data["gt_masks"].cpu()
+    c0, l0 = torch_ref.sample_prompts_eval(data["coords"].cpu(), gt, None)
+    assert torch.equal(c0, pcs[0]) and torch.equal(l0, pls[0].bool())
+    c1, l1 = torch_ref.sample_prompts_eval(data["coords"].cpu(), gt, want[0]["prompt_masks"])
+    assert torch.equal(c1, pcs[1]) and torch.equal(l1, pls[1].bool())
+    iou0 = float(compute_iou(outs[0]["prompt_masks"], data["gt_masks"].flatten(0, 1)).mean())
+    assert 0.0 <= iou0 <= 1.0
+    # ---- demo session ----
+    model.pc_encoder.patch_embed.grouper.num_groups, model.pc_encoder.patch_embed.grouper.group_size = 32, 16
+    g.num_groups, g.group_size = 32, 16
+    xyz, feats = synth.make_batch(1, 600, 60, "ball")
+    pts = np.concatenate([xyz[0].numpy() * 4 + 1, np.round((feats[0].numpy() * 0.5 + 0.5) * 255)], axis=1)
+    scene = tmp_path / "scene.ply"
+    scene.write_text("ply\nformat ascii 1.0\nelement vertex 600\nproperty float x\nproperty float y\nproperty float z\n"
+                     "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n" +
+                     "\n".join("%f %f %f %d %d %d" % tuple(r) for r in pts) + "\n")
+    sess = SegmentSession(model, device=d, output_dir=str(tmp_path / "results"))
+    resp = sess.pointcloud(str(scene))
+    assert len(resp["xyz"]) == 1800 and len(resp["rgb"]) == 1800
+    nxyz = np.array(resp["xyz"], dtype=np.float64).reshape(-1, 3)
+    assert abs(np.linalg.norm(nxyz, axis=1).max() - 1.0) < 1e-9
+    cached = model._cloud
+    n0 = nv.LAUNCHES[0]
+    r1 = sess.segment({"prompt_point": nxyz[10].tolist(), "prompt_label": 1})
+    first = nv.LAUNCHES[0] - n0
+    assert len(r1["seg"]) == 600 and isinstance(r1["seg"][0], bool)
+    cx, cf = torch.from_numpy(nxyz).float()[None], torch.from_numpy(np.array(resp["rgb"]).reshape(-1, 3)).float()[None]
+    pp, pl = cx[:, 10:11], torch.ones(1, 1, dtype=torch.long)
+    with torch.no_grad():
+        m, s = oracle.predict_masks(cx, cf, pp, pl, None, True)
+    b = int(torch.argmax(s[0]))
+    np.testing.assert_allclose(sess.prompt_mask.cpu().numpy()[0], m[0, b].numpy(), atol=ATOL, rtol=RTOL)
+    stable = m[0, b].abs() > 5e-3  # sign of logits this close to 0 is not comparable
+    assert np.array_equal(np.array(r1["seg"])[stable.numpy()], (m[0, b] > 0).numpy()[stable.numpy()])
+    n1 = nv.LAUNCHES[0]
+    r2 = sess.segment({"prompt_point": nxyz[200].tolist(), "prompt_label": 0})
+    second = nv.LAUNCHES[0] - n1
+    assert len(r2["seg"]) == 600 and len(sess.prompts) == 2
+    # clicks reuse the embeddings computed when the cloud was loaded (the reference re-encodes on every click)
+    assert model._cloud is cached and first < 100 and second < 100, (first, second)
+    assert sess.next() == {"status": "cleared"} and len(sess.masks) == 1 and sess.prompts == []
+    assert sess.save() == {"status": "saved"} and os.path.exists(str(tmp_path / "results" / "scene.npy"))
+    assert sess.clear() == {"status": "cleared"}
