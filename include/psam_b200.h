@@ -68,7 +68,7 @@ int psam_nn_distance_f32(const float* query, const float* key, int n1, int n2, f
                          cudaStream_t stream);
 
 /* Batched ground-truth prompt sampler: replaces the per-(cloud, mask) Python loops of sample_fixed_points /
- * sample_furthest_points_from_border (pc_sam/model/common.py:371-474) and their chamfer_distance calls with two launches
+ * sample_furthest_points_from_border (pc_sam/model/common.py:371-474) and their chamfer_distance calls with four launches
  * and no host synchronisation.  gt_masks [B*M, N] (0/1 bytes); prediction either as logits (mask = logit > 0,
  * common.py:392) or as 0/1 bytes (thresholded by the caller), or both NULL (first iteration: pred_logits is None).
  * from_error_region != 0: sample the point of (fn | fp) farthest from its complement (common.py:402-410);
@@ -76,8 +76,10 @@ int psam_nn_distance_f32(const float* query, const float* key, int n1, int n2, f
  * Distances and tie-breaks equal the reference's (chamfer arithmetic, torch.argmax = lowest index).
  * Outputs: prompt_xyz_out [B*M, 3], prompt_label_out [B*M] (the ground-truth value at the sampled point), *status is
  * set to 1 if some mask had no valid candidate (the reference raises in torch.stack there); the caller zeroes it.
- * workspace: psam_border_prompt_workspace_bytes(B, M) bytes. */
-size_t psam_border_prompt_workspace_bytes(int B, int M);
+ * workspace: psam_border_prompt_workspace_bytes(B, M, N) bytes, 4-byte aligned (region counters, compacted foreground /
+ * background index lists and per-point minima: the distance sweep costs |fg| x |bg| evaluations like the reference's
+ * compacted chamfer call, spread over (fg block x background chunk) thread blocks). */
+size_t psam_border_prompt_workspace_bytes(int B, int M, int N);
 int psam_border_prompt_f32(const float* coords, const unsigned char* gt_masks, const float* pred_logits,
                            const unsigned char* pred_masks, int B, int M, int N, int from_error_region,
                            float* prompt_xyz_out, unsigned char* prompt_label_out, int* status, void* workspace,

@@ -346,71 +346,117 @@ __device__ __forceinline__ int border_region_label(int region, int mode, bool gt
     return gt ? 1 : 0;
 }
 
-__global__ void __launch_bounds__(256)
-border_farthest_kernel(const float* __restrict__ coords, const unsigned char* __restrict__ gt, const float* __restrict__ logits,
-                       const unsigned char* __restrict__ pred_mask, int M, int N, int mode,
-                       unsigned long long* __restrict__ best /* [BM][3] */) {
-    __shared__ float s_k[256 * 3];
-    __shared__ unsigned char s_lab[256];
-    __shared__ unsigned long long s_best[8];
-    const int bm = blockIdx.z, region = blockIdx.y;
-    const float* xyz = coords + (size_t)(bm / M) * N * 3;
-    const unsigned char* g = gt + (size_t)bm * N;
-    const float* lg = logits ? logits + (size_t)bm * N : nullptr;
-    const unsigned char* pmk = pred_mask ? pred_mask + (size_t)bm * N : nullptr;
-    auto label_of = [&](int j) {
-        const bool p = lg ? (lg[j] > 0.f) : (pmk ? pmk[j] != 0 : false);
-        return border_region_label(region, mode, g[j] != 0, p);
-    };
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    float x = 0.f, y = 0.f, z = 0.f;
-    int mine = 0;
-    if (i < N) {
-        x = xyz[(size_t)i * 3], y = xyz[(size_t)i * 3 + 1], z = xyz[(size_t)i * 3 + 2];
-        mine = label_of(i);
-    }
-    if (!__syncthreads_or(mine)) return;  // no foreground point in this block
-    float bestd = 3.4e38f;
-    bool any_bg = false;
-    for (int j0 = 0; j0 < N; j0 += 256) {
-        const int j = j0 + threadIdx.x;
-        if (j < N) {
-            s_k[threadIdx.x * 3] = xyz[(size_t)j * 3];
-            s_k[threadIdx.x * 3 + 1] = xyz[(size_t)j * 3 + 1];
-            s_k[threadIdx.x * 3 + 2] = xyz[(size_t)j * 3 + 2];
-            s_lab[threadIdx.x] = (unsigned char)label_of(j);
-        }
-        __syncthreads();
-        const int lim = min(256, N - j0);
-        for (int t = 0; t < lim; ++t) {
-            if (s_lab[t] == 0) {  // uniform across the block: no divergence
-                any_bg = true;
-                bestd = fminf(bestd, sqdist3(s_k[t * 3], s_k[t * 3 + 1], s_k[t * 3 + 2], x, y, z));
-            }
-        }
-        __syncthreads();
-    }
-    unsigned long long key = 0ull;
-    if (mine && any_bg) key = ((unsigned long long)__float_as_uint(bestd) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-        key = other > key ? other : key;
-    }
-    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = key;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) key = s_best[w] > key ? s_best[w] : key;
-        if (key) atomicMax(best + (size_t)bm * 3 + region, key);
+// Pass 1: compact the foreground AND background point indices of every (cloud x mask, region) - order is irrelevant because
+// min() is order independent and the arg-max key carries the original index.  Warp-aggregated append (one atomic per warp
+// and list); the per-point minimum is initialised to +inf on the way.
+__device__ __forceinline__ void warp_append(bool pred, int value, int* counter, int* list, unsigned* init_inf) {
+    const int lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) {
+        const int slot = base + __popc(m & ((1u << lane) - 1));
+        list[slot] = value;
+        if (init_inf) init_inf[slot] = 0x7f800000u;
     }
 }
 
-__global__ void border_select_kernel(const float* __restrict__ coords, const unsigned char* __restrict__ gt,
-                                     const unsigned long long* __restrict__ best, int BM, int M, int N, int mode,
-                                     float* __restrict__ out_xyz, unsigned char* __restrict__ out_label, int* __restrict__ status) {
-    const int bm = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bm >= BM) return;
-    const unsigned long long p = best[(size_t)bm * 3], n = best[(size_t)bm * 3 + 1], g = best[(size_t)bm * 3 + 2];
+__global__ void __launch_bounds__(256)
+border_compact_kernel(const unsigned char* __restrict__ gt, const float* __restrict__ logits,
+                      const unsigned char* __restrict__ pred_mask, int N, int mode, int nreg, int* __restrict__ counts /* [BM][3][2] */,
+                      int* __restrict__ fg_list, int* __restrict__ bg_list, unsigned* __restrict__ mind /* each [BM][nreg][N] */) {
+    const int bm = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    bool g = false, p = false;
+    if (i < N) {
+        g = gt[(size_t)bm * N + i] != 0;
+        p = logits ? (logits[(size_t)bm * N + i] > 0.f) : (pred_mask ? pred_mask[(size_t)bm * N + i] != 0 : false);
+    }
+    for (int r = 0; r < nreg; ++r) {
+        const int lab = border_region_label(r, mode, g, p);
+        const size_t off = ((size_t)bm * nreg + r) * N;
+        warp_append(i < N && lab == 1, i, counts + (bm * 3 + r) * 2, fg_list + off, mind + off);
+        warp_append(i < N && lab == 0, i, counts + (bm * 3 + r) * 2 + 1, bg_list + off, nullptr);
+    }
+}
+
+// Pass 2: block = 512 foreground points (2 per thread) x one chunk of BORDER_CHUNK background points, staged through
+// shared memory as float4 (one LDS.128 feeds two distance evaluations).  |fg| x |bg| evaluations in total - the same
+// work as the reference's compacted chamfer call - spread over enough blocks to fill the GPU for a single mask.
+constexpr int BORDER_CHUNK = 2048;
+
+__global__ void __launch_bounds__(256)
+border_mindist_kernel(const float* __restrict__ coords, int M, int N, int nreg, const int* __restrict__ counts,
+                      const int* __restrict__ fg_list, const int* __restrict__ bg_list, unsigned* __restrict__ mind) {
+    __shared__ float4 s_b[256];
+    const int br = blockIdx.z, bm = br / nreg, region = br - bm * nreg;
+    const int nfg = counts[(bm * 3 + region) * 2], nbg = counts[(bm * 3 + region) * 2 + 1];
+    const int f0 = blockIdx.x * 512, c0 = blockIdx.y * BORDER_CHUNK;
+    if (f0 >= nfg || c0 >= nbg) return;
+    const float* xyz = coords + (size_t)(bm / M) * N * 3;
+    const size_t off = (size_t)br * N;
+    const int s0 = f0 + threadIdx.x, s1 = s0 + 256;
+    const int i0 = s0 < nfg ? fg_list[off + s0] : 0, i1 = s1 < nfg ? fg_list[off + s1] : 0;
+    const float x0 = xyz[(size_t)i0 * 3], y0 = xyz[(size_t)i0 * 3 + 1], z0 = xyz[(size_t)i0 * 3 + 2];
+    const float x1 = xyz[(size_t)i1 * 3], y1 = xyz[(size_t)i1 * 3 + 1], z1 = xyz[(size_t)i1 * 3 + 2];
+    float m0 = __int_as_float(0x7f800000), m1 = m0;
+    const int c1 = min(c0 + BORDER_CHUNK, nbg);
+    for (int j0 = c0; j0 < c1; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        if (j < c1) {
+            const int k = bg_list[off + j];
+            s_b[threadIdx.x] = make_float4(xyz[(size_t)k * 3], xyz[(size_t)k * 3 + 1], xyz[(size_t)k * 3 + 2], 0.f);
+        }
+        __syncthreads();
+        const int lim = min(256, c1 - j0);
+#pragma unroll 4
+        for (int t = 0; t < lim; ++t) {
+            const float4 b = s_b[t];
+            m0 = fminf(m0, sqdist3(b.x, b.y, b.z, x0, y0, z0));
+            m1 = fminf(m1, sqdist3(b.x, b.y, b.z, x1, y1, z1));
+        }
+        __syncthreads();
+    }
+    if (s0 < nfg) atomicMin(mind + off + s0, __float_as_uint(m0));  // distances are >= 0: uint order == float order
+    if (s1 < nfg) atomicMin(mind + off + s1, __float_as_uint(m1));
+}
+
+// Pass 3: one block per (cloud x mask): arg-max of the per-point minima in each region (ties -> lowest point index, like
+// torch.argmax over the compacted array), then the reference's selection rules (common.py:411-431).
+__global__ void __launch_bounds__(256)
+border_select_kernel(const float* __restrict__ coords, const unsigned char* __restrict__ gt, const int* __restrict__ counts,
+                     const int* __restrict__ fg_list, const unsigned* __restrict__ mind, int M, int N, int mode, int nreg,
+                     float* __restrict__ out_xyz, unsigned char* __restrict__ out_label, int* __restrict__ status) {
+    __shared__ unsigned long long s_best[8];
+    __shared__ unsigned long long s_reg[3];
+    const int bm = blockIdx.x;
+    for (int r = 0; r < nreg; ++r) {
+        const int nfg = counts[(bm * 3 + r) * 2], nbg = counts[(bm * 3 + r) * 2 + 1];
+        const size_t off = ((size_t)bm * nreg + r) * N;
+        unsigned long long key = 0ull;
+        if (nbg > 0)
+            for (int s_ = threadIdx.x; s_ < nfg; s_ += 256) {
+                const unsigned long long k = ((unsigned long long)mind[off + s_] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)fg_list[off + s_]);
+                key = k > key ? k : key;
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+        }
+        if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = key;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) key = s_best[w] > key ? s_best[w] : key;
+            s_reg[r] = key;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    const unsigned long long p = s_reg[0], n = nreg > 1 ? s_reg[1] : 0ull, g = nreg > 2 ? s_reg[2] : 0ull;
     const float pd = p ? __uint_as_float((unsigned)(p >> 32)) : -1.f;
     const float nd = n ? __uint_as_float((unsigned)(n >> 32)) : -1.f;
     unsigned long long pick;
@@ -432,7 +478,11 @@ __global__ void border_select_kernel(const float* __restrict__ coords, const uns
 
 }  // namespace psam
 
-extern "C" size_t psam_border_prompt_workspace_bytes(int B, int M) { return (size_t)B * M * 3 * sizeof(unsigned long long); }
+// workspace layout: counts[BM][3][2] i32 | fg_list, bg_list [BM][3][N] i32 | mind[BM][3][N] u32
+extern "C" size_t psam_border_prompt_workspace_bytes(int B, int M, int N) {
+    const size_t bm = (size_t)B * M;
+    return bm * 6 * 4 + bm * 3 * (size_t)N * 4 * 3;
+}
 
 extern "C" int psam_border_prompt_f32(const float* coords, const unsigned char* gt_masks, const float* pred_logits,
                                       const unsigned char* pred_masks, int B, int M, int N, int from_error_region,
@@ -440,18 +490,25 @@ extern "C" int psam_border_prompt_f32(const float* coords, const unsigned char* 
                                       cudaStream_t stream) {
     using namespace psam;
     if (!coords || !gt_masks || !prompt_xyz_out || !prompt_label_out || !status || !workspace || B <= 0 || M <= 0 || N <= 0 ||
-        (pred_logits && pred_masks))
+        (pred_logits && pred_masks) || ((uintptr_t)workspace & 3) != 0)
         return PSAM_ERR_ARG;
-    if ((long long)B * M > 65535) return PSAM_ERR_UNSUPPORTED;
+    if ((long long)B * M * 3 > 65535) return PSAM_ERR_UNSUPPORTED;
     const int BM = B * M;
     const int mode = from_error_region ? 0 : 1;
-    unsigned long long* best = static_cast<unsigned long long*>(workspace);
-    PSAM_CUDA_TRY(cudaMemsetAsync(best, 0, psam_border_prompt_workspace_bytes(B, M), stream));
-    border_farthest_kernel<<<dim3(ceil_div(N, 256), mode == 0 ? 1 : 3, BM), 256, 0, stream>>>(coords, gt_masks, pred_logits, pred_masks, M, N,
-                                                                                            mode, best);
+    const int nreg = mode == 0 ? 1 : 3;
+    int* counts = static_cast<int*>(workspace);
+    int* fg_list = counts + (size_t)BM * 6;
+    int* bg_list = fg_list + (size_t)BM * 3 * N;
+    unsigned* mind = reinterpret_cast<unsigned*>(bg_list + (size_t)BM * 3 * N);
+    PSAM_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)BM * 6 * 4, stream));
+    border_compact_kernel<<<dim3(ceil_div(N, 256), BM), 256, 0, stream>>>(gt_masks, pred_logits, pred_masks, N, mode, nreg, counts, fg_list,
+                                                                         bg_list, mind);
     PSAM_LAUNCH_CHECK();
-    border_select_kernel<<<ceil_div(BM, 128), 128, 0, stream>>>(coords, gt_masks, best, BM, M, N, mode, prompt_xyz_out, prompt_label_out,
-                                                                status);
+    border_mindist_kernel<<<dim3(ceil_div(N, 512), ceil_div(N, BORDER_CHUNK), BM * nreg), 256, 0, stream>>>(coords, M, N, nreg, counts, fg_list,
+                                                                                                          bg_list, mind);
+    PSAM_LAUNCH_CHECK();
+    border_select_kernel<<<BM, 256, 0, stream>>>(coords, gt_masks, counts, fg_list, mind, M, N, mode, nreg, prompt_xyz_out, prompt_label_out,
+                                                 status);
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }

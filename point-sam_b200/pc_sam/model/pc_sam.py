@@ -100,6 +100,13 @@ class PointCloudSAM(nn.Module):
 
         return PipelinedPredictor(self, batch_size, num_points, num_prompts, depth, multimask_output, use_graph)
 
+    def make_iterative_predictor(self, batch_size: int, num_masks: int, num_points: int, use_graph: bool = True):
+        """forward(is_eval=True) - encoder, then `prompt_iters` rounds of (GT prompt sampling, prompt / mask encoders,
+        decoder, best-mask feedback) - captured as ONE CUDA graph with no host synchronisation inside."""
+        from psam_b200.predictor import IterativeGraphPredictor
+
+        return IterativeGraphPredictor(self, batch_size, num_masks, num_points, use_graph)
+
     # ------------------------------------------------------------------------------------------
     def predict_iterative(self, coords, features, prompt_coords_seq: List[torch.Tensor],
                           prompt_labels_seq: List[torch.Tensor]) -> List[Dict[str, torch.Tensor]]:

@@ -4,7 +4,7 @@ sample_furthest_points_from_border).  SURVEY.md section 8(f) rank 1 ("next" row)
 
 The reference walks (cloud, mask) pairs in Python, compacts foreground/background points, calls torkit3d's chamfer
 kernel per region and compares the results on the host.  Here every (cloud, mask, region) is evaluated by one
-psam_border_prompt_f32 call (two launches, no host synchronisation except the single validity check), with the same
+psam_border_prompt_f32 call (compact, distance sweep, select; no host synchronisation except the single validity check), with the same
 distances (chamfer arithmetic) and the same argmax tie-break."""
 from __future__ import annotations
 
@@ -12,7 +12,7 @@ from typing import Union
 
 import torch
 
-from psam_b200 import ops
+from psam_b200 import engine, ops
 
 
 def sample_furthest_points_from_border(coords: torch.Tensor, labels: torch.Tensor, gt: torch.Tensor):
@@ -37,9 +37,9 @@ def sample_fixed_points(points, gt_masks, pred_logits, threshold=None, from_erro
             logits = pred_logits  # mask = logit > 0, evaluated inside the kernel
         else:
             masks = pred_logits.sigmoid() > threshold
-    xyz, labels, status = ops.border_prompt(points, gt_masks.bool(), logits, masks, from_error_region)
-    if int(status.item()):  # the one host check per prompt iteration
-        raise RuntimeError("prompt sampling: a ground-truth mask is empty or covers the whole cloud (no border to sample from)")
+    xyz, labels, _ = ops.border_prompt(points, gt_masks.bool(), logits, masks, from_error_region,
+                                       status=engine.sampler_flag(points.device))
+    engine.raise_if_sampler_failed(points.device)  # the one host check per prompt iteration (skipped under graph capture)
     return xyz, labels
 
 

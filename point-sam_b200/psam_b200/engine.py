@@ -304,6 +304,29 @@ def raise_if_out_of_range(device):
         raise ValueError("Input coordinates must be normalized to [-1, 1].")
 
 
+_sampler_flags = {}
+
+
+def sampler_flag(device) -> torch.Tensor:
+    """Sticky device flag set by psam_border_prompt_f32 when a mask has no border to sample from."""
+    f = _sampler_flags.get(device)
+    if f is None:
+        f = torch.zeros(1, dtype=torch.int32, device=device)
+        _sampler_flags[device] = f
+    return f
+
+
+def raise_if_sampler_failed(device):
+    """The reference fails in torch.stack([... None ...]) (common.py:433); checked once per prompt iteration, or once
+    per replay when the loop runs as a CUDA graph."""
+    if torch.cuda.is_current_stream_capturing():
+        return
+    f = sampler_flag(device)
+    if int(f.item()) != 0:
+        f.zero_()
+        raise RuntimeError("prompt sampling: a ground-truth mask is empty or covers the whole cloud (no border to sample from)")
+
+
 def run_pos_embedding(pe_layer, coords, labels=None, emb0=None, emb1=None, check=True):
     c = coords.float().contiguous()
     lab = labels.to(torch.int32).contiguous() if labels is not None else None

@@ -75,7 +75,7 @@ def lib():
         L.psam_fps_workspace_bytes.argtypes = [i, i, i]
         L.psam_version.restype = ctypes.c_char_p
         L.psam_border_prompt_workspace_bytes.restype = c_size_t
-        L.psam_border_prompt_workspace_bytes.argtypes = [i, i]
+        L.psam_border_prompt_workspace_bytes.argtypes = [i, i, i]
         sig = {
             "psam_fps_f32": [p, i, i, i, p, p, p, p],
             "psam_knn_f32": [p, p, i, i, i, i, p, p, p],

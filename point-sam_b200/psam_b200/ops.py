@@ -100,7 +100,8 @@ def nn_distance(query: torch.Tensor, key: torch.Tensor):
 
 
 def border_prompt(coords: torch.Tensor, gt_masks: torch.Tensor, pred_logits: Optional[torch.Tensor] = None,
-                  pred_masks: Optional[torch.Tensor] = None, from_error_region: bool = False):
+                  pred_masks: Optional[torch.Tensor] = None, from_error_region: bool = False,
+                  status: Optional[torch.Tensor] = None):
     """Batched farthest-from-border prompt sampling (psam_border_prompt_f32).  coords [B,N,3], gt_masks [B,M,N] bool,
     prediction as logits [B*M,N] or bool masks [B*M,N] or neither.  Returns (xyz [B*M,1,3], labels [B*M,1] bool, status)."""
     B, M, N = gt_masks.shape
@@ -113,8 +114,9 @@ def border_prompt(coords: torch.Tensor, gt_masks: torch.Tensor, pred_logits: Opt
     dev = c.device
     xyz = torch.empty((B * M, 1, 3), dtype=torch.float32, device=dev)
     lab = torch.empty((B * M, 1), dtype=torch.uint8, device=dev)
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
-    ws = torch.empty(nv.lib().psam_border_prompt_workspace_bytes(B, M), dtype=torch.uint8, device=dev)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(nv.lib().psam_border_prompt_workspace_bytes(B, M, N), dtype=torch.uint8, device=dev)
     nv.check(nv.lib().psam_border_prompt_f32(nv.ptr(c), nv.ptr(g), nv.ptr(lg), nv.ptr(pm), B, M, N, int(from_error_region), nv.ptr(xyz),
                                              nv.ptr(lab), nv.ptr(status), nv.ptr(ws), nv.stream()), "border_prompt")
     return xyz, lab.view(torch.bool), status

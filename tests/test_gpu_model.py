@@ -304,3 +304,47 @@ def test_eval_driver_and_demo_session(tmp_path):
     assert sess.next() == {"status": "cleared"} and len(sess.masks) == 1 and sess.prompts == []
     assert sess.save() == {"status": "saved"} and os.path.exists(str(tmp_path / "results" / "scene.npy"))
     assert sess.clear() == {"status": "cleared"}
+
+
+def test_iterative_graph_predictor_matches_eager_forward():
+    """forward(is_eval=True) replayed as one CUDA graph (encoder + all prompt iterations, sampler included)."""
+    model, oracle = _build("eva02_test_tiny", 32, 16, 11)
+    d = torch.device("cuda:0")
+    B, M, N = 2, 2, 1500
+    model.prompt_iters = 3
+    pred = model.make_iterative_predictor(B, M, N)
+    clouds = []
+    for s_ in (0, 1):
+        xyz, feats = synth.make_batch(B, N, 90 + s_)
+        gt = torch.stack([torch.stack([xyz[b, :, (m + s_) % 3] > 0.1 * m for m in range(M)]) for b in range(B)])
+        clouds.append((xyz.to(d), feats.to(d), gt.to(d)))
+    pred.warmup(*clouds[0])
+    assert pred.graph is not None and pred.launches_per_step > 0
+    for c in (clouds[1], clouds[0]):
+        with torch.no_grad():
+            want = model(*c, is_eval=True)
+        got = pred(*c)
+        assert len(got) == 3
+        for t in range(3):
+            assert torch.equal(got[t]["prompt_coords"], want[t]["prompt_coords"])
+            assert torch.equal(got[t]["prompt_labels"], want[t]["prompt_labels"])
+            assert got[t]["masks"].shape == (B * M, 3 if t == 0 else 1, N)
+            torch.testing.assert_close(got[t]["masks"], want[t]["masks"], atol=2e-4, rtol=1e-4)
+            torch.testing.assert_close(got[t]["prompt_masks"], want[t]["prompt_masks"], atol=2e-4, rtol=1e-4)
+    # oracle replay of the last cloud with the sampled prompts
+    xyz, feats, gt = clouds[0]
+    pcs = [got[0]["prompt_coords"].cpu()] + [got[t]["prompt_coords"][:, t:t + 1].cpu() for t in (1, 2)]
+    pls = [got[0]["prompt_labels"].cpu()] + [got[t]["prompt_labels"][:, t:t + 1].cpu() for t in (1, 2)]
+    oracle.prompt_iters = 3
+    with torch.no_grad():
+        ow = oracle.predict_iterative(xyz.cpu(), feats.cpu(), pcs, pls)
+    for t in range(3):
+        np.testing.assert_allclose(got[t]["masks"].cpu().numpy(), ow[t]["masks"].numpy(), atol=ATOL, rtol=RTOL)
+    # deferred validity checks still fire (after the replay)
+    bad = clouds[0][2].clone()
+    bad[0, 1] = True
+    with pytest.raises(RuntimeError):
+        pred(clouds[0][0], clouds[0][1], bad)
+    with pytest.raises(ValueError):
+        pred(clouds[0][0] * 4, clouds[0][1], clouds[0][2])
+    pred(*clouds[0])  # flags were reset: a valid cloud passes again

@@ -15,8 +15,13 @@ from pc_sam.model import build_point_sam  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="c2")
 ap.add_argument("--passes", type=int, default=1)
+ap.add_argument("--throughput-tiles", action="store_true", help="tile policy of the pipelined predictor (BN=256)")
 a = ap.parse_args()
 enc, N, G, K, bpg, P, kind = CONFIGS[a.config]
+if a.throughput_tiles:
+    from psam_b200 import ops
+
+    ops.GEMM_TILE_HINT = 1
 dev = torch.device("cuda:0")
 torch.manual_seed(1234)
 model = build_point_sam(enc, G, K).to(dev).eval()
