@@ -285,6 +285,270 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Long sequences (L > 512: the reference evaluation runs group_number = 2048, evaluation/eval_kitti.py:352-362).
+// S no longer fits the tensor memory, so the row is swept twice over 128-key blocks, still with an EXACT softmax:
+//   sweep 1: S_j = Q K_j^T -> running row maximum only (no exponentials, no P, no PV)
+//   sweep 2: S_j recomputed -> P_j = exp2(S_j * c - m * c) with the final maximum -> O += P_j V_j, row sum
+// (1.5x the tensor work of one-sweep attention, no rescaling of O and no second exponential pass).
+// TMEM: O in columns [0,64); a ring of three 128-column S slots at columns 128/256/384, so the tensor pipe runs up to two
+// key blocks ahead of the softmax warps.  Shared memory and the warp roles are those of attention_tc_kernel.
+constexpr int ATT_SLOTS = 3;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                         const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t q_full, p_full, p_empty, o_full;
+    __shared__ __align__(8) uint64_t kv_full[ATT_STAGES], kv_empty[ATT_STAGES];
+    __shared__ __align__(8) uint64_t s_full[ATT_SLOTS], s_empty[ATT_SLOTS];
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t sQ = smem_base;
+    const uint32_t sKV = sQ + ATT_SMEM_Q;
+    const uint32_t sP = sKV + ATT_STAGES * ATT_SMEM_STAGE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int nkb = (p.L + ATT_BKEY - 1) / ATT_BKEY;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+        mbar_init(smem_u32(&q_full), 1);
+        mbar_init(smem_u32(&p_full), 256);
+        mbar_init(smem_u32(&p_empty), 1);
+        mbar_init(smem_u32(&o_full), 1);
+        for (int s = 0; s < ATT_STAGES; ++s) {
+            mbar_init(smem_u32(&kv_full[s]), 1);
+            mbar_init(smem_u32(&kv_empty[s]), 1);
+        }
+        for (int s = 0; s < ATT_SLOTS; ++s) {
+            mbar_init(smem_u32(&s_full[s]), 1);
+            mbar_init(smem_u32(&s_empty[s]), 256);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    // Order in which the stage ring carries the operand blocks; the MMA warp consumes them in exactly this order:
+    //   K_0 .. K_{nkb-1}                                   (sweep 1)
+    //   K_0, K_1, then (K_{j+2}, V_j) for j = 0 .. nkb-1    (sweep 2; K runs two blocks ahead of V)
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t qb = smem_u32(&q_full);
+            mbar_arrive_expect_tx(qb, ATT_SMEM_Q);
+            tma_load_5d(sQ, &tmap_q, qb, 0, q_tile * ATT_BQ, 0, h, b);
+            int i = 0;
+            auto load = [&](const CUtensorMap* tm, int blk) {
+                const int s = i % ATT_STAGES;
+                mbar_wait(smem_u32(&kv_empty[s]), ((uint32_t)(i / ATT_STAGES) & 1u) ^ 1u);
+                const uint32_t fb = smem_u32(&kv_full[s]);
+                mbar_arrive_expect_tx(fb, ATT_SMEM_STAGE);
+                tma_load_5d(sKV + s * ATT_SMEM_STAGE, tm, fb, 0, blk * ATT_BKEY, 0, h, b);
+                ++i;
+            };
+            for (int j = 0; j < nkb; ++j) load(&tmap_k, j);
+            load(&tmap_k, 0);
+            if (nkb > 1) load(&tmap_k, 1);
+            for (int j = 0; j < nkb; ++j) {
+                if (j + 2 < nkb) load(&tmap_k, j + 2);
+                load(&tmap_v, j);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, ATT_BKEY);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_DH) | (1u << 16);
+        mbar_wait(smem_u32(&q_full), 0);
+        tc_fence_after();
+        const uint64_t q_hi = umma_desc_k_sw128(sQ), q_lo = umma_desc_k_sw128(sQ + ATT_TILE);
+        const uint64_t p_hi = umma_desc_k_sw128(sP), p_lo = umma_desc_k_sw128(sP + 2 * ATT_TILE);
+        int i = 0;  // stage-ring item counter (same sequence as the producer)
+        auto issue_s = [&](int g) {  // S block number g (0 .. 2*nkb-1) into slot g % 3
+            const int s = i % ATT_STAGES, slot = g % ATT_SLOTS;
+            mbar_wait(smem_u32(&kv_full[s]), (uint32_t)(i / ATT_STAGES) & 1u);
+            if (g >= ATT_SLOTS) mbar_wait(smem_u32(&s_empty[slot]), (uint32_t)(g / ATT_SLOTS - 1) & 1u);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sk = sKV + s * ATT_SMEM_STAGE;
+                const uint64_t k_hi = umma_desc_k_sw128(sk), k_lo = umma_desc_k_sw128(sk + ATT_TILE);
+                const uint32_t d_s = tmem_base + 128u + (uint32_t)(slot * ATT_BKEY);
+#pragma unroll
+                for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_hi + 2 * k, k_hi + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_lo + 2 * k, k_hi + 2 * k, idesc_s, 1u);
+#pragma unroll
+                for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_hi + 2 * k, k_lo + 2 * k, idesc_s, 1u);
+                umma_commit(smem_u32(&kv_empty[s]));
+                umma_commit(smem_u32(&s_full[slot]));
+            }
+            __syncwarp();
+            ++i;
+        };
+        for (int g = 0; g < nkb; ++g) issue_s(g);
+        issue_s(nkb);
+        if (nkb > 1) issue_s(nkb + 1);
+        for (int j = 0; j < nkb; ++j) {
+            if (j + 2 < nkb) issue_s(nkb + j + 2);
+            const int s = i % ATT_STAGES;
+            mbar_wait(smem_u32(&kv_full[s]), (uint32_t)(i / ATT_STAGES) & 1u);
+            mbar_wait(smem_u32(&p_full), (uint32_t)j & 1u);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sv = sKV + s * ATT_SMEM_STAGE;
+                const uint64_t v_hi = umma_desc_mn_sw128(sv), v_lo = umma_desc_mn_sw128(sv + ATT_TILE);
+#pragma unroll
+                for (int ks = 0; ks < ATT_BKEY / 16; ++ks) {
+                    const uint64_t pa = (uint64_t)((ks >> 2) * (ATT_TILE >> 4) + (ks & 3) * 2);
+                    const uint64_t va = (uint64_t)(ks * (2048 >> 4));
+                    umma_bf16(tmem_base, p_hi + pa, v_hi + va, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int ks = 0; ks < ATT_BKEY / 16; ++ks) {
+                    const uint64_t pa = (uint64_t)((ks >> 2) * (ATT_TILE >> 4) + (ks & 3) * 2);
+                    const uint64_t va = (uint64_t)(ks * (2048 >> 4));
+                    umma_bf16(tmem_base, p_lo + pa, v_hi + va, idesc_o, 1u);
+                }
+#pragma unroll
+                for (int ks = 0; ks < ATT_BKEY / 16; ++ks) {
+                    const uint64_t pa = (uint64_t)((ks >> 2) * (ATT_TILE >> 4) + (ks & 3) * 2);
+                    const uint64_t va = (uint64_t)(ks * (2048 >> 4));
+                    umma_bf16(tmem_base, p_hi + pa, v_lo + va, idesc_o, 1u);
+                }
+                umma_commit(smem_u32(&kv_empty[s]));
+                umma_commit(smem_u32(&p_empty));
+                if (j == nkb - 1) umma_commit(smem_u32(&o_full));
+            }
+            __syncwarp();
+            ++i;
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int sub = (warp - 2) >> 2;
+        const int r = quarter * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float* xchg = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn)) + ATT_SMEM_Q + ATT_STAGES * ATT_SMEM_STAGE +
+                                               ATT_SMEM_P);
+        // ---- sweep 1: row maximum ----
+        float mx = -3.0e38f;
+        for (int g = 0; g < nkb; ++g) {
+            const int slot = g % ATT_SLOTS;
+            mbar_wait(smem_u32(&s_full[slot]), (uint32_t)(g / ATT_SLOTS) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = sub; c < ATT_BKEY / 32; c += 2) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + 128u + (uint32_t)(slot * ATT_BKEY + c * 32), v);
+                tmem_ld_wait();
+                const int key0 = g * ATT_BKEY + c * 32;
+                if (key0 + 32 <= p.L) {
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(v[t]));
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 32; ++t)
+                        if (key0 + t < p.L) mx = fmaxf(mx, __uint_as_float(v[t]));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&s_empty[slot]));
+        }
+        xchg[sub * 128 + r] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(mx, xchg[(sub ^ 1) * 128 + r]);
+        const float mscaled = mx * p.scale_log2e;
+        // ---- sweep 2: P_j and the row sum ----
+        float lsum = 0.f;
+        for (int j = 0; j < nkb; ++j) {
+            const int g = nkb + j, slot = g % ATT_SLOTS;
+            mbar_wait(smem_u32(&s_full[slot]), (uint32_t)(g / ATT_SLOTS) & 1u);
+            if (j > 0) mbar_wait(smem_u32(&p_empty), (uint32_t)(j - 1) & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = sub; c < ATT_BKEY / 32; c += 2) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_row + 128u + (uint32_t)(slot * ATT_BKEY + c * 32), v);
+                tmem_ld_wait();
+                const int key0 = j * ATT_BKEY + c * 32;
+                const bool full = key0 + 32 <= p.L;
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int t = 0; t < 32; t += 2) {
+                    float e0, e1;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(v[t]), p.scale_log2e, -mscaled)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(v[t + 1]), p.scale_log2e, -mscaled)));
+                    if (!full) {
+                        if (key0 + t >= p.L) e0 = 0.f;
+                        if (key0 + t + 1 >= p.L) e1 = 0.f;
+                    }
+                    lsum += e0 + e1;
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+                    const float2 hf = __bfloat1622float2(h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(e0 - hf.x, e1 - hf.y);
+                    hi[t >> 1] = *reinterpret_cast<const uint32_t*>(&h2);
+                    lo[t >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                const uint32_t rowbase = (uint32_t)((c >> 1) * ATT_TILE + r * 128);
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const uint32_t chunk = (uint32_t)(((c & 1) * 4 + q4) ^ (r & 7));
+                    st_shared_v4(sP + rowbase + chunk * 16, hi[q4 * 4], hi[q4 * 4 + 1], hi[q4 * 4 + 2], hi[q4 * 4 + 3]);
+                    st_shared_v4(sP + 2 * ATT_TILE + rowbase + chunk * 16, lo[q4 * 4], lo[q4 * 4 + 1], lo[q4 * 4 + 2], lo[q4 * 4 + 3]);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            mbar_arrive(smem_u32(&s_empty[slot]));
+            mbar_arrive(smem_u32(&p_full));
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        xchg[sub * 128 + r] = lsum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        lsum += xchg[(sub ^ 1) * 128 + r];
+        mbar_wait(smem_u32(&o_full), 0);
+        tc_fence_after();
+        const int qrow = q_tile * ATT_BQ + r;
+        const float inv = 1.0f / lsum;
+        __nv_bfloat16* ohi = p.out_hi + (long long)b * p.out_b + (long long)h * p.out_h + (long long)qrow * p.ldo;
+        __nv_bfloat16* olo = ohi + p.out_plane;
+        {
+            const int c = sub;
+            uint32_t v[32];
+            tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+            if (qrow < p.L) {
+#pragma unroll
+                for (int t = 0; t < 32; t += 8) {
+                    uint32_t hh[4], ll[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        split_bf16(__uint_as_float(v[t + 2 * u]) * inv, h0, l0);
+                        split_bf16(__uint_as_float(v[t + 2 * u + 1]) * inv, h1, l1);
+                        hh[u] = pack_bf16x2(h0, h1);
+                        ll[u] = pack_bf16x2(l0, l1);
+                    }
+                    *reinterpret_cast<uint4*>(ohi + c * 32 + t) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                    *reinterpret_cast<uint4*>(olo + c * 32 + t) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 int make_operand_map_ext(CUtensorMap* map, const psam_operand* op, int box_rows, int box_planes);  // gemm_tc.cu
 
 }  // namespace psam
@@ -296,7 +560,7 @@ extern "C" int psam_attention_bf16x3(const psam_operand* q, const psam_operand* 
     if (!q || !k || !v || !out_hi) return PSAM_ERR_ARG;
     const int L = q->rows, dh = q->k;
     const int H = q->nb1 > 0 ? q->nb1 : 1, B = q->nb2 > 0 ? q->nb2 : 1;
-    if (dh != ATT_DH || L > 512 || L <= 0) return PSAM_ERR_UNSUPPORTED;
+    if (dh != ATT_DH || L <= 0) return PSAM_ERR_UNSUPPORTED;
     if (k->rows != L || v->rows != L || k->k != dh || v->k != dh) return PSAM_ERR_ARG;
     if ((ldo | out_plane | out_head_stride | out_cloud_stride) & 7) return PSAM_ERR_ARG;
     CUtensorMap mq, mk, mv;
@@ -311,8 +575,14 @@ extern "C" int psam_attention_bf16x3(const psam_operand* q, const psam_operand* 
     p.scale_log2e = scale * 1.4426950408889634f;
     p.out_hi = (__nv_bfloat16*)out_hi;
     p.out_plane = out_plane, p.ldo = ldo, p.out_h = out_head_stride, p.out_b = out_cloud_stride;
-    PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
     dim3 grid((unsigned)ceil_div(L, ATT_BQ), (unsigned)H, (unsigned)B);
+    if (L > 512) {  // two-sweep kernel: S streamed through a ring of TMEM slots
+        PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
+        attention_tc_long_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, stream>>>(mq, mk, mv, p);
+        PSAM_LAUNCH_CHECK();
+        return PSAM_OK;
+    }
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
     PSAM_CUDA_TRY(psam::launch(attention_tc_kernel, dim3(grid), dim3(ATT_THREADS), (size_t)(ATT_SMEM_TOTAL), stream, mq, mk, mv, p));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;

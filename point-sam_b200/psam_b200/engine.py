@@ -19,6 +19,7 @@ from . import ops
 from .ops import ACT_GELU, ACT_NONE, ACT_RELU, Split
 
 FUSED_ATTENTION = True
+FUSED_ATTENTION_LONG = os.environ.get("PSAM_FUSED_ATTENTION_LONG", "1") != "0"
 FUSED_MASK_DOT = os.environ.get("PSAM_FUSED_MASK_DOT", "1") != "0"
 PASSES = 3  # split-bf16 (fp32-parity) mode; 1 = plain bf16 (fails the 1e-3 parity bound)
 
@@ -191,7 +192,7 @@ class _PackedEncoder:
 
 
 def _attention_unfused(qkv: Split, att: Split, B: int, L: int, H: int, dh: int, D: int, dev):
-    """Fallback for head dims / sequence lengths the fused kernel does not cover (EVA-giant dh=88, L > 512)."""
+    """Fallback for head dims the fused kernels do not cover (EVA-giant dh=88)."""
     # V^T per (cloud, head): [B, H, dh, Lp]
     Lp = (L + 63) // 64 * 64
     vt = Split(B * H * dh, L, dev, pitch=Lp, zero=(Lp != L))
@@ -227,8 +228,9 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
     qkv = Split(M, 3 * D, dev)
     ops.gemm(xn, pb.wqkv, bias=pb.bqkv, out_split=qkv, passes=PASSES)
     att = Split(M, D, dev)
-    if FUSED_ATTENTION and dh == 64 and L <= 512:
-        # fused tcgen05 attention: S stays in tensor memory, V^T is read as an MN-major operand
+    if FUSED_ATTENTION and dh == 64 and (L <= 512 or FUSED_ATTENTION_LONG):
+        # fused tcgen05 attention: S stays in tensor memory (L <= 512) or streams through a ring of TMEM slots in two
+        # sweeps (longer rows); V^T is read as an MN-major operand
         mk = lambda col: qkv.operand(rows=L, k=dh, col=col, nb1=H, b1_stride=dh, nb2=B, b2_stride=L * qkv.pitch)
         qa, ka, va = mk(0), mk(D), mk(2 * D)
         nv.check(nv.lib().psam_attention_bf16x3(byref(qa), byref(ka), byref(va), att.ptr(), att.plane, att.pitch, dh,

@@ -368,9 +368,10 @@ def test_linear_attention_posenc_misc():
     torch.testing.assert_close(got.reshape(4, 48), want, atol=0, rtol=0)
 
 
-@pytest.mark.parametrize("B,H,L", [(1, 16, 512), (2, 3, 128), (2, 2, 200), (1, 4, 333), (1, 2, 64)])
+@pytest.mark.parametrize("B,H,L", [(1, 16, 512), (2, 3, 128), (2, 2, 200), (1, 4, 333), (1, 2, 64),
+                                   (1, 2, 640), (2, 3, 1000), (1, 16, 2048), (1, 1, 513), (1, 2, 3000)])
 def test_fused_attention_tc(B, H, L):
-    """psam_attention_bf16x3 (S in TMEM, exact softmax, MN-major V) vs fp64 softmax attention."""
+    """psam_attention_bf16x3 (S in TMEM, exact softmax, MN-major V; two-sweep ring kernel for L > 512) vs fp64 attention."""
     from ctypes import byref
 
     from psam_b200 import native as nv
