@@ -22,15 +22,18 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--points", type=int, default=32768)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--encoder", default="eva02_large_patch14_448")
+ap.add_argument("--groups", type=int, default=512)
+ap.add_argument("--group-size", type=int, default=64)
+ap.add_argument("--kind", default="ball")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(1234)
-model = build_point_sam(a.encoder, 512, 64).to(dev).eval()
+model = build_point_sam(a.encoder, a.groups, a.group_size).to(dev).eval()
 model.prompt_iters = a.iters
 B, M, N = a.clouds, a.masks, a.points
 data = []
 for s in range(2):
-    xyz, feats = synth.make_batch(B, N, 300 + s, "ball")
+    xyz, feats = synth.make_batch(B, N, 300 + s, a.kind)
     gt = torch.stack([torch.stack([(xyz[b] - xyz[b, 997 * (m + 1)]).norm(dim=-1) < 0.45 + 0.05 * m for m in range(M)]) for b in range(B)])
     data.append(tuple(t.to(dev) for t in (xyz, feats, gt)))
 
@@ -59,7 +62,7 @@ out = pred(*data[0])
 from pc_sam.model.loss import compute_iou  # noqa: E402
 
 ious = [float(compute_iou(o["prompt_masks"], data[0][2].flatten(0, 1)).mean()) for o in out]
-print(json.dumps({"workload": f"{B} clouds x {M} mask(s), N={N}, {a.encoder}, {a.iters} prompt iterations (forward(is_eval=True))",
+print(json.dumps({"workload": f"{B} clouds x {M} mask(s), N={N}, G={a.groups}, K={a.group_size}, {a.encoder}, {a.iters} prompt iterations (forward(is_eval=True))",
                   "eager_ms_per_step": ms_eager, "graph_ms_per_step": ms_graph, "graph_ms_per_step_no_host_check": ms_graph_nocheck,
                   "clouds_per_s_eager": B / ms_eager * 1e3, "clouds_per_s_graph": B / ms_graph * 1e3,
                   "launches_per_step": pred.launches_per_step, "iou_vs_gt_random_weights": ious}))
