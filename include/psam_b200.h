@@ -163,6 +163,8 @@ typedef struct {
     float* y; long long ldy;                  /* optional */
     void* y_hi; long long y_plane, ldy_s, pitch; /* optional split output */
     int padded;                               /* 1: x rows (zeros), gamma, beta and outputs are valid up to roundup4(D) */
+    int policy;                               /* 0: lowest latency (CTA per row for short token streams); 1: least SM-time
+                                               * (warp per row, no block barriers) - used when several clouds are in flight */
 } psam_ln_args;
 int psam_layernorm_f32(const psam_ln_args* args, cudaStream_t stream);
 

@@ -49,7 +49,7 @@ class LnArgs(Structure):
                 ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float),
                 ("rows", c_int), ("D", c_int), ("act", c_int),
                 ("y", c_void_p), ("ldy", c_longlong),
-                ("y_hi", c_void_p), ("y_plane", c_longlong), ("ldy_s", c_longlong), ("pitch", c_longlong), ("padded", c_int)]
+                ("y_hi", c_void_p), ("y_plane", c_longlong), ("ldy_s", c_longlong), ("pitch", c_longlong), ("padded", c_int), ("policy", c_int)]
 
 
 EXPORTS = [

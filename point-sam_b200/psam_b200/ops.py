@@ -201,6 +201,7 @@ def layernorm(x, gamma, beta, eps, *, rows=None, D=None, r=None, gbias=None, gro
     if out_split is not None:
         a.y_hi, a.y_plane, a.ldy_s, a.pitch = out_split.ptr(), out_split.plane, out_split.pitch, out_split.pitch
     a.padded = int(padded)
+    a.policy = GEMM_TILE_HINT  # same switch as the GEMM tile policy: 1 while capturing the pipelined predictor's graphs
     nv.check(nv.lib().psam_layernorm_f32(byref(a), nv.stream()), "layernorm")
 
 

@@ -279,6 +279,19 @@ def test_layernorm_variants():
     ops.layernorm(x, g, b, 1e-5, gbias=t, group_rows=100, act=ops.ACT_GELU, out_f32=out)
     want = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x + t.repeat_interleave(100, 0), (2730,), g, b, 1e-5))
     torch.testing.assert_close(out, want, atol=2e-5, rtol=1e-5)
+    # the ViT token stream (512 x 1024 / 768) under both launch policies: CTA per row (latency) / warp per row (SM-time)
+    for D in (1024, 768, 256):
+        x1, r1, g1, b1 = _rand(512, D, seed=6), _rand(512, D, seed=7), _rand(D, seed=8), _rand(D, seed=9)
+        want = torch.nn.functional.layer_norm(x1 + r1, (D,), g1, b1, 1e-6)
+        for policy in (0, 1):
+            prev, ops.GEMM_TILE_HINT = ops.GEMM_TILE_HINT, policy
+            try:
+                o1, s1 = torch.empty_like(x1), ops.Split(512, D, _dev())
+                ops.layernorm(x1, g1, b1, 1e-6, r=r1, out_f32=o1, out_split=s1)
+            finally:
+                ops.GEMM_TILE_HINT = prev
+            torch.testing.assert_close(o1, want, atol=2e-5, rtol=1e-5)
+            assert float((s1.float() - want).abs().max()) < 1e-4
 
 
 def test_swiglu_small_in_groupmax_softmax_transpose():
