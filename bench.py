@@ -112,7 +112,7 @@ def cpu_reference_throughput(cfg, steps: int, warmup: int):
     return steps * bpg / tot, tot / steps * 1e3, torch.get_num_threads()
 
 
-def gpu_reference_throughput(cfg, steps: int, warmup: int):
+def gpu_reference_throughput(cfg, steps: int, warmup: int, model=None):
     """SURVEY.md 8(d) "GPU reference beside it": the reference's own GPU execution model on this box - its FPS kernel
     compiled for sm_100a (oracle/_ref, when it travelled) + cdist/topk + PyTorch fp32 eager modules (the oracle
     restatement moved to cuda:0).  A reported comparison point only (like cpu_baseline); nothing here is product code."""
@@ -127,9 +127,22 @@ def gpu_reference_throughput(cfg, steps: int, warmup: int):
     out = {"fps": "reference kernel (oracle/_ref)" if ref is not None else "oracle C port on the host (oracle/_ref absent)",
            "kind": "reference execution model: torkit3d FPS + cdist/topk + PyTorch eager modules, same GPU", "steps": steps}
     try:
+        ours = model
         model = torch_ref.build_model(enc, G, K, seed=1234).to(dev)
         clouds = [tuple(t.to(dev) for t in synth.make_batch(bpg, N, 0 + 17 * i, kind)) for i in range(2)]
         prompts = [tuple(t.to(dev) for t in synth.make_prompts(c[0].cpu(), P, i)) for i, c in enumerate(clouds)]
+        if ours is not None:
+            # full-size parity on this very workload: same weights, same cloud, fp32 eager oracle vs the CUDA path
+            model.load_state_dict(ours.state_dict(), strict=True)
+            with torch.no_grad():
+                want_m, want_i = model.predict_masks(*clouds[0], *prompts[0], None, True)
+                got_m, got_i = ours.predict_masks(*clouds[0], *prompts[0], None, True)
+            err = (got_m - want_m).abs()
+            out["parity"] = {"max_abs_err_logits": float(err.max()), "mean_abs_err_logits": float(err.mean()),
+                             "logit_range": [float(want_m.min()), float(want_m.max())],
+                             "max_abs_err_iou": float((got_i - want_i).abs().max()),
+                             "within_1e-3_abs_plus_1e-2_rel": bool((err <= 1e-3 + 1e-2 * want_m.abs()).all()),
+                             "sign_agreement": float(((got_m > 0) == (want_m > 0)).float().mean())}
         for tag, tf32 in (("fp32", False), ("tf32", True)):
             torch.backends.cuda.matmul.allow_tf32 = tf32
             with torch.no_grad():
@@ -457,7 +470,7 @@ def main():
                                               "(C restatement of the FPS kernel + PyTorch fp32 CPU path, all host threads)"}
         if world == 1 and not args.no_gpu_reference:
             try:
-                line["gpu_reference"] = gpu_reference_throughput(cfg, 10, 3)
+                line["gpu_reference"] = gpu_reference_throughput(cfg, 10, 3, model)
             except Exception as e:  # a comparison figure must never break the bench line
                 line["gpu_reference"] = {"unavailable": repr(e)[:160]}
         print(json.dumps(line), flush=True)

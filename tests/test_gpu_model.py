@@ -348,3 +348,22 @@ def test_iterative_graph_predictor_matches_eager_forward():
     with pytest.raises(ValueError):
         pred(clouds[0][0] * 4, clouds[0][1], clouds[0][2])
     pred(*clouds[0])  # flags were reset: a valid cloud passes again
+
+
+def test_config2_full_size_vs_fp32_oracle_on_gpu():
+    """BASELINE config[1] at full size (N=32768, group_number=512, group_size=64, EVA02-L, 24 blocks): the CUDA path
+    against the fp32 PyTorch oracle evaluated on the same GPU (cuBLAS fp32, TF32 off), same weights and inputs."""
+    d = torch.device("cuda:0")
+    enc, G, K, N = "eva02_large_patch14_448", 512, 64, 32768
+    model, oracle = _build(enc, G, K, 21)
+    xyz, feats = synth.make_batch(1, N, 33)
+    pc, pl = synth.make_prompts(xyz, 1, 33)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    oracle = oracle.to(d)
+    args = [t.to(d) for t in (xyz, feats, pc, pl)]
+    with torch.no_grad():
+        want_m, want_i = oracle.predict_masks(*args, None, True)  # FPS through the C oracle on the host
+        got_m, got_i = model.predict_masks(*args)
+    _report("c2 full size", got_m, want_m)
+    np.testing.assert_allclose(got_m.cpu().numpy(), want_m.cpu().numpy(), atol=ATOL, rtol=RTOL)
+    np.testing.assert_allclose(got_i.cpu().numpy(), want_i.cpu().numpy(), atol=ATOL, rtol=RTOL)
