@@ -23,6 +23,7 @@
 // tile count fits the 148 SMs in as few waves as possible.
 #include <stdlib.h>
 
+#include <cstdlib>
 #include "psam_common.cuh"
 #include "../../include/psam_b200.h"
 
@@ -51,6 +52,7 @@ struct GemmEpilogue {
     const float* rd_w;   // optional fused row-dot: rd_out[z, c, n] += sum_col act(x[z*rd_rows + n, col]) * rd_w[z, c, col]
     float* rd_out;       // (pre-zeroed; the hyper-network mask product of the decoder), rd_rows % 32 == 0, rd_c <= 8
     int rd_rows, rd_c;
+    int vec4;  // host-verified: every output / bias / residual row is 16-byte (split planes: 8-byte) addressable in 4-column steps
 };
 
 struct GemmShape {
@@ -169,6 +171,96 @@ __device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
     else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+// ---- vectorised epilogue (fast path) -------------------------------------------------------------------------------
+// One 32-row x 32-column chunk per call.  Staging is a 128-bit transpose through shared memory: thread = row writes its 32
+// accumulators as 8 STS.128 (row pitch 36 floats: conflict-free), then lane (rsub = lane/8, cg = lane%8) reads rows
+// rsub, rsub+4, ... as float4 at columns 4*cg..4*cg+3, so every global instruction of the warp covers 4 rows x 128
+// contiguous bytes.  8 LDS.128 + 8 STG.128 (or 16 STG.64 for the split planes) per chunk instead of 32 + 32 scalar ones:
+// the scalar epilogue issued ~0.9 warp-instructions per output element and bounded the small-K GEMMs of the mini-PointNet.
+constexpr int EPI_PITCH = 36;  // floats per staged row
+enum EpiMode { EPI_F32 = 0, EPI_ACC = 1, EPI_SPLIT = 2, EPI_SPLIT_F32 = 3, EPI_SWIGLU = 4, EPI_NONE = 5 };
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+template <int ACT, bool RES, int MODE>
+__device__ __forceinline__ void epi_chunk_v4(float* __restrict__ stg, const uint32_t (&v)[32], int lane, int row0, int M, int col0,
+                                             const GemmEpilogue& ep, bool add_bias, float* out, const float* res,
+                                             __nv_bfloat16* ohi) {
+    float4* srow = reinterpret_cast<float4*>(stg + lane * EPI_PITCH);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        srow[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                              __uint_as_float(v[4 * q + 3]));
+    __syncwarp();
+    const int cg = lane & 7, rsub = lane >> 3;
+    const int col = col0 + cg * 4;
+    const float4 b4 = add_bias ? ld4(ep.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float alpha = ep.alpha;
+    const float ninf = __int_as_float(0xff800000);
+    float4 mx = make_float4(ninf, ninf, ninf, ninf);
+    __nv_bfloat16* olo = ohi ? ohi + ep.out_plane : nullptr;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + rsub, row = row0 + rr;
+        float4 x = ld4(stg + rr * EPI_PITCH + cg * 4);
+        x.x = fmaf(x.x, alpha, b4.x), x.y = fmaf(x.y, alpha, b4.y), x.z = fmaf(x.z, alpha, b4.z), x.w = fmaf(x.w, alpha, b4.w);
+        if (row < M) {
+            if (ep.gmax) mx.x = fmaxf(mx.x, x.x), mx.y = fmaxf(mx.y, x.y), mx.z = fmaxf(mx.z, x.z), mx.w = fmaxf(mx.w, x.w);
+            if (MODE == EPI_NONE) continue;
+            if (RES) {
+                const float4 r4 = ld4(res + (long long)row * ep.ldo + col);
+                x.x += r4.x, x.y += r4.y, x.z += r4.z, x.w += r4.w;
+            }
+            x.x = apply_act(x.x, ACT), x.y = apply_act(x.y, ACT), x.z = apply_act(x.z, ACT), x.w = apply_act(x.w, ACT);
+            if (MODE == EPI_F32 || MODE == EPI_SPLIT_F32) *reinterpret_cast<float4*>(out + (long long)row * ep.ldo + col) = x;
+            if (MODE == EPI_ACC) atomicAdd(reinterpret_cast<float4*>(out + (long long)row * ep.ldo + col), x);
+            if (MODE == EPI_SWIGLU)
+                *reinterpret_cast<float2*>(out + (long long)row * ep.ldo + (col >> 1)) =
+                    make_float2(__fdividef(x.x, 1.0f + __expf(-x.x)) * x.y, __fdividef(x.z, 1.0f + __expf(-x.z)) * x.w);
+            if (MODE == EPI_SPLIT || MODE == EPI_SPLIT_F32) {
+                __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+                split_bf16(x.x, h0, l0);
+                split_bf16(x.y, h1, l1);
+                split_bf16(x.z, h2, l2);
+                split_bf16(x.w, h3, l3);
+                const long long o = (long long)row * ep.ldo_s + col;
+                *reinterpret_cast<uint2*>(ohi + o) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+                *reinterpret_cast<uint2*>(olo + o) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+            }
+        }
+    }
+    if (ep.gmax) {
+        // rows of this chunk belong to one group: combine the 4 row sub-sets, then 8 lanes x 4 columns of atomics
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, o));
+            mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, o));
+            mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, o));
+            mx.w = fmaxf(mx.w, __shfl_xor_sync(0xffffffffu, mx.w, o));
+        }
+        if (rsub == 0 && row0 < M) {
+            float* g = ep.gmax + (long long)(row0 / ep.group_rows) * ep.ld_gmax + col;
+            atomic_max_f32(g, mx.x), atomic_max_f32(g + 1, mx.y), atomic_max_f32(g + 2, mx.z), atomic_max_f32(g + 3, mx.w);
+        }
+    }
+}
+
+template <int ACT>
+__device__ __forceinline__ void epi_chunk_v4_dispatch(float* stg, const uint32_t (&v)[32], int lane, int row0, int M, int col0,
+                                                      const GemmEpilogue& ep, bool add_bias, float* out, const float* res,
+                                                      __nv_bfloat16* ohi) {
+#define PSAM_V4(R, MODE) epi_chunk_v4<ACT, R, MODE>(stg, v, lane, row0, M, col0, ep, add_bias, out, res, ohi)
+    if (ep.swiglu) PSAM_V4(false, EPI_SWIGLU);
+    else if (ep.accumulate) PSAM_V4(false, EPI_ACC);
+    else if (ohi && out) { if (res) PSAM_V4(true, EPI_SPLIT_F32); else PSAM_V4(false, EPI_SPLIT_F32); }
+    else if (ohi) { if (res) PSAM_V4(true, EPI_SPLIT); else PSAM_V4(false, EPI_SPLIT); }
+    else if (out) { if (res) PSAM_V4(true, EPI_F32); else PSAM_V4(false, EPI_F32); }
+    else PSAM_V4(false, EPI_NONE);
+#undef PSAM_V4
+}
+
+
 // Shared epilogue of the 1-CTA and 2-CTA kernels: TMEM -> registers (thread = row) -> per-warp smem transpose ->
 // coalesced global accesses (lane = column: every store/load/red touches one contiguous 128-byte row segment).
 __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const GemmEpilogue& ep, unsigned char* smem_aligned,
@@ -181,7 +273,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const Gemm
             tc_fence_after();
         }
         // All TMA loads have landed and all MMAs have retired: the pipeline stages are free to reuse.
-        float* stg = reinterpret_cast<float*>(smem_aligned) + (warp - 2) * (32 * 33);
+        float* stg = reinterpret_cast<float*>(smem_aligned) + (warp - 2) * (32 * EPI_PITCH);  // 16-byte aligned rows
         const int ehalf = (warp - 2) >> 2;  // the warps of a lane quarter take interleaved 32-column chunks
         const long long obase = (long long)b1 * ep.out_b1 + (long long)b2 * ep.out_b2;
         float* out = ep.out_f32 ? ep.out_f32 + obase : nullptr;
@@ -227,6 +319,13 @@ __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const Gemm
                     for (int cc = 0; cc < 8; ++cc)
                         if (cc < ep.rd_c) atomicAdd(o + (long long)cc * ep.rd_rows, accd[cc]);
                 }
+                continue;
+            }
+            if (ep.vec4 && col0 + 32 <= shape.N) {
+                if (ep.swiglu || ep.accumulate || ep.act == ACT_NONE)
+                    epi_chunk_v4_dispatch<ACT_NONE>(stg, v, lane, row0, shape.M, col0, ep, add_bias, out, res, ohi);
+                else if (ep.act == ACT_GELU) epi_chunk_v4_dispatch<ACT_GELU>(stg, v, lane, row0, shape.M, col0, ep, add_bias, out, res, ohi);
+                else epi_chunk_v4_dispatch<ACT_RELU>(stg, v, lane, row0, shape.M, col0, ep, add_bias, out, res, ohi);
                 continue;
             }
             __syncwarp();
@@ -727,6 +826,17 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     ep.swiglu = o->swiglu;
     ep.gmax = o->gmax, ep.ld_gmax = o->ld_gmax, ep.group_rows = o->group_rows;
     ep.rd_w = o->rd_w, ep.rd_out = o->rd_out, ep.rd_rows = o->rd_rows, ep.rd_c = o->rd_c;
+    {
+        auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+        auto a8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
+        static const bool off = getenv("PSAM_GEMM_SCALAR_EPILOGUE") != nullptr;
+        bool ok = !off && !ep.rd_out && (!ep.bias || a16(ep.bias));
+        if (ep.out_f32) ok = ok && a16(ep.out_f32) && ((ep.ldo | ep.out_b1 | ep.out_b2) & 3) == 0;
+        if (ep.resid) ok = ok && a16(ep.resid);
+        if (ep.out_hi) ok = ok && a8(ep.out_hi) && ((ep.ldo_s | ep.out_plane | ep.outs_b1 | ep.outs_b2) & 3) == 0;
+        if (ep.gmax) ok = ok && ep.group_rows % 32 == 0;
+        ep.vec4 = ok ? 1 : 0;
+    }
     if (ep.rd_out && (!ep.rd_w || ep.rd_rows <= 0 || ep.rd_rows % 32 || ep.rd_c <= 0 || ep.rd_c > 8 || ep.accumulate || ep.resid || ep.swiglu ||
                       ep.gmax || ep.out_f32 || ep.out_hi || split_k != 1 || sh.nb1 * sh.nb2 != 1)) return PSAM_ERR_ARG;
     if (ep.gmax && (ep.group_rows <= 0 || ep.group_rows % 32 || ep.accumulate || ep.resid || ep.act || ep.swiglu || sh.nb1 * sh.nb2 != 1)) return PSAM_ERR_ARG;

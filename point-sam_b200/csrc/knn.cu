@@ -134,20 +134,16 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ key, int Q
     // ---- B. collect candidates d2 <= tau -------------------------------------------------------
     // Four consecutive points per thread and step, fetched as three coalesced 128-bit loads (12 floats): 4x fewer load
     // instructions than point-wise access and all of them independent, so the sweep is no longer latency-bound.
+    // Hits are rare (about K * sample_stride of N points): one shared-memory atomic per hit is cheaper than a
+    // warp-aggregated append whose vote / popc / shuffle sequence every lane would execute for every point.
     auto append = [&](bool hit, float d, int j) {
-        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_ncand, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (hit) {
-                const int pos = base + __popc(m & ((1u << lane) - 1u));
-                if (pos < cap) {
-                    c_d2[pos] = d;
-                    c_idx[pos] = j;
-                } else {
-                    s_overflow = 1;
-                }
+        if (hit) {
+            const int pos = atomicAdd(&s_ncand, 1);
+            if (pos < cap) {
+                c_d2[pos] = d;
+                c_idx[pos] = j;
+            } else {
+                s_overflow = 1;
             }
         }
     };

@@ -1,0 +1,64 @@
+"""Launch one hot kernel in isolation between cudaProfilerStart/Stop (for `ncu --profile-from-start off --set full`).
+usage: python tools/kernel_once.py {attention_long|attention|knn|knn_c4|border|gemm_qkv|gemm_pe}"""
+import os
+import sys
+from ctypes import byref
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (REPO, os.path.join(REPO, "point-sam_b200")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+from oracle import synth  # noqa: E402  (synthetic inputs only)
+from psam_b200 import native as nv, ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+what = sys.argv[1]
+
+
+def attention(L, H=16, B=1, dh=64):
+    D = H * dh
+    qkv = ops.Split(B * L, 3 * D, dev)
+    qkv.t.normal_()
+    att = ops.Split(B * L, D, dev)
+    mk = lambda col: qkv.operand(rows=L, k=dh, col=col, nb1=H, b1_stride=dh, nb2=B, b2_stride=L * qkv.pitch)
+    qa, ka, va = mk(0), mk(D), mk(2 * D)
+    return lambda: nv.check(nv.lib().psam_attention_bf16x3(byref(qa), byref(ka), byref(va), att.ptr(), att.plane, att.pitch, dh,
+                                                           L * att.pitch, dh ** -0.5, nv.stream()), "attention")
+
+
+def knn(N, G, K, kind):
+    xyz, _ = synth.make_batch(1, N, 5, kind)
+    x = xyz.to(dev)
+    idx, centers = ops.fps(x, G)
+    return lambda: ops.knn(centers, x, K)
+
+
+def border(N):
+    xyz, _ = synth.make_batch(1, N, 6, "ball")
+    gt = ((xyz[0] - xyz[0, 997]).norm(dim=-1) < 0.45)[None, None]
+    g = torch.Generator().manual_seed(7)
+    pred = (gt.reshape(1, N).float() * 2 - 1) * (torch.rand(1, N, generator=g) * 2 - 0.3)
+    x, gt, pred = xyz.to(dev), gt.to(dev), pred.to(dev)
+    return lambda: ops.border_prompt(x, gt, pred, None, False)
+
+
+def gemm(M, N, K, hint):
+    a, w = ops.Split(M, K, dev), ops.Split(N, K, dev)
+    a.t.normal_()
+    w.t.normal_()
+    out = torch.zeros(M, N, device=dev)
+    ops.GEMM_TILE_HINT = hint
+    return lambda: ops.gemm(a, w, out_f32=out, passes=3)
+
+
+fn = {"attention_long": lambda: attention(2048), "attention": lambda: attention(512), "knn": lambda: knn(32768, 512, 64, "ball"),
+      "knn_c4": lambda: knn(131072, 2048, 256, "kitti"), "border": lambda: border(32768), "gemm_qkv": lambda: gemm(512, 3072, 1024, 1),
+      "gemm_pe": lambda: gemm(32768, 512, 128, 1)}[what]()
+for _ in range(3):
+    fn()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+fn()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
