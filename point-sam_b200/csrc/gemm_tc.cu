@@ -52,6 +52,10 @@ struct GemmEpilogue {
     const float* rd_w;   // optional fused row-dot: rd_out[z, c, n] += sum_col act(x[z*rd_rows + n, col]) * rd_w[z, c, col]
     float* rd_out;       // (pre-zeroed; the hyper-network mask product of the decoder), rd_rows % 32 == 0, rd_c <= 8
     int rd_rows, rd_c;
+    float* stats_out;        // SwiGLU + split output: stats_out[row] += (sum, sum of squares) of the fp32 products of the row
+    const float* ln_stats;   // LayerNorm folded into THIS GEMM: A holds the un-normalised rows, W is pre-scaled by gamma;
+    const float* ln_c;       //   out = rstd * (acc - mean * ln_c[n]) + bias[n]  (bias = W beta + b), stats = (sum, sum sq) per row
+    float ln_inv_h, ln_eps;
     int vec4;  // host-verified: every output / bias / residual row is 16-byte (split planes: 8-byte) addressable in 4-column steps
 };
 
@@ -178,7 +182,7 @@ __device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
 // contiguous bytes.  8 LDS.128 + 8 STG.128 (or 16 STG.64 for the split planes) per chunk instead of 32 + 32 scalar ones:
 // the scalar epilogue issued ~0.9 warp-instructions per output element and bounded the small-K GEMMs of the mini-PointNet.
 constexpr int EPI_PITCH = 36;  // floats per staged row
-enum EpiMode { EPI_F32 = 0, EPI_ACC = 1, EPI_SPLIT = 2, EPI_SPLIT_F32 = 3, EPI_SWIGLU = 4, EPI_NONE = 5 };
+enum EpiMode { EPI_F32 = 0, EPI_ACC = 1, EPI_SPLIT = 2, EPI_SPLIT_F32 = 3, EPI_SWIGLU = 4, EPI_NONE = 5, EPI_SWIGLU_SPLIT = 6 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
@@ -196,6 +200,7 @@ __device__ __forceinline__ void epi_chunk_v4(float* __restrict__ stg, const uint
     const int cg = lane & 7, rsub = lane >> 3;
     const int col = col0 + cg * 4;
     const float4 b4 = add_bias ? ld4(ep.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 c4 = ep.ln_stats ? ld4(ep.ln_c + col) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float alpha = ep.alpha;
     const float ninf = __int_as_float(0xff800000);
     float4 mx = make_float4(ninf, ninf, ninf, ninf);
@@ -204,7 +209,43 @@ __device__ __forceinline__ void epi_chunk_v4(float* __restrict__ stg, const uint
     for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + rsub, row = row0 + rr;
         float4 x = ld4(stg + rr * EPI_PITCH + cg * 4);
-        x.x = fmaf(x.x, alpha, b4.x), x.y = fmaf(x.y, alpha, b4.y), x.z = fmaf(x.z, alpha, b4.z), x.w = fmaf(x.w, alpha, b4.w);
+        if (MODE == EPI_SWIGLU_SPLIT) {
+            // product of the (gate, value) pairs -> split-bf16 planes + per-row (sum, sum of squares) for the LayerNorm that
+            // the consuming GEMM applies algebraically (the reference normalises silu(g)*x before fc2, timm SwiGLU.norm)
+            x.x = fmaf(x.x, alpha, b4.x), x.y = fmaf(x.y, alpha, b4.y), x.z = fmaf(x.z, alpha, b4.z), x.w = fmaf(x.w, alpha, b4.w);
+            const bool ok = row < M;
+            const float p0 = ok ? __fdividef(x.x, 1.0f + __expf(-x.x)) * x.y : 0.f;
+            const float p1 = ok ? __fdividef(x.z, 1.0f + __expf(-x.z)) * x.w : 0.f;
+            float s1 = p0 + p1, s2 = fmaf(p0, p0, p1 * p1);
+#pragma unroll
+            for (int o = 1; o <= 4; o <<= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (ok) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                split_bf16(p0, h0, l0);
+                split_bf16(p1, h1, l1);
+                const long long o = (long long)row * ep.ldo_s + (col >> 1);
+                *reinterpret_cast<uint32_t*>(ohi + o) = pack_bf16x2(h0, h1);
+                *reinterpret_cast<uint32_t*>(olo + o) = pack_bf16x2(l0, l1);
+                if (cg == 0 && ep.stats_out) {
+                    atomicAdd(ep.stats_out + 2 * (long long)row, s1);
+                    atomicAdd(ep.stats_out + 2 * (long long)row + 1, s2);
+                }
+            }
+            continue;
+        }
+        if (ep.ln_stats) {
+            const float2 st = row < M ? *reinterpret_cast<const float2*>(ep.ln_stats + 2 * (long long)row) : make_float2(0.f, 1.f);
+            const float mean = st.x * ep.ln_inv_h;
+            const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, st.y * ep.ln_inv_h), 0.f) + ep.ln_eps);
+            const float ra = rstd * alpha, mr = add_bias ? -mean * rstd : 0.f;
+            x.x = fmaf(x.x, ra, fmaf(mr, c4.x, b4.x)), x.y = fmaf(x.y, ra, fmaf(mr, c4.y, b4.y));
+            x.z = fmaf(x.z, ra, fmaf(mr, c4.z, b4.z)), x.w = fmaf(x.w, ra, fmaf(mr, c4.w, b4.w));
+        } else {
+            x.x = fmaf(x.x, alpha, b4.x), x.y = fmaf(x.y, alpha, b4.y), x.z = fmaf(x.z, alpha, b4.z), x.w = fmaf(x.w, alpha, b4.w);
+        }
         if (row < M) {
             if (ep.gmax) mx.x = fmaxf(mx.x, x.x), mx.y = fmaxf(mx.y, x.y), mx.z = fmaxf(mx.z, x.z), mx.w = fmaxf(mx.w, x.w);
             if (MODE == EPI_NONE) continue;
@@ -251,7 +292,8 @@ __device__ __forceinline__ void epi_chunk_v4_dispatch(float* stg, const uint32_t
                                                       const GemmEpilogue& ep, bool add_bias, float* out, const float* res,
                                                       __nv_bfloat16* ohi) {
 #define PSAM_V4(R, MODE) epi_chunk_v4<ACT, R, MODE>(stg, v, lane, row0, M, col0, ep, add_bias, out, res, ohi)
-    if (ep.swiglu) PSAM_V4(false, EPI_SWIGLU);
+    if (ep.swiglu && ohi) PSAM_V4(false, EPI_SWIGLU_SPLIT);
+    else if (ep.swiglu) PSAM_V4(false, EPI_SWIGLU);
     else if (ep.accumulate) PSAM_V4(false, EPI_ACC);
     else if (ohi && out) { if (res) PSAM_V4(true, EPI_SPLIT_F32); else PSAM_V4(false, EPI_SPLIT_F32); }
     else if (ohi) { if (res) PSAM_V4(true, EPI_SPLIT); else PSAM_V4(false, EPI_SPLIT); }
@@ -837,10 +879,21 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
         if (ep.gmax) ok = ok && ep.group_rows % 32 == 0;
         ep.vec4 = ok ? 1 : 0;
     }
+    ep.stats_out = o->stats_out, ep.ln_stats = o->ln_stats, ep.ln_c = o->ln_c;
+    ep.ln_inv_h = o->ln_h > 0 ? 1.0f / (float)o->ln_h : 0.f, ep.ln_eps = o->ln_eps;
+    // the fused forms exist only in the vectorised epilogue: whole 32-column chunks, aligned rows
+    if ((ep.swiglu && ep.out_hi) || ep.ln_stats) {
+        if (!ep.vec4 || sh.N % 32 != 0 || sh.nb1 * sh.nb2 != 1) return PSAM_ERR_UNSUPPORTED;
+        if (ep.ln_stats && (!ep.ln_c || o->ln_h <= 0 || ep.swiglu || ep.gmax || ep.act || ep.out_hi ||
+                            (reinterpret_cast<uintptr_t>(ep.ln_c) & 15) || (reinterpret_cast<uintptr_t>(ep.ln_stats) & 7)))
+            return PSAM_ERR_ARG;
+    } else if (ep.stats_out) {
+        return PSAM_ERR_ARG;
+    }
     if (ep.rd_out && (!ep.rd_w || ep.rd_rows <= 0 || ep.rd_rows % 32 || ep.rd_c <= 0 || ep.rd_c > 8 || ep.accumulate || ep.resid || ep.swiglu ||
                       ep.gmax || ep.out_f32 || ep.out_hi || split_k != 1 || sh.nb1 * sh.nb2 != 1)) return PSAM_ERR_ARG;
     if (ep.gmax && (ep.group_rows <= 0 || ep.group_rows % 32 || ep.accumulate || ep.resid || ep.act || ep.swiglu || sh.nb1 * sh.nb2 != 1)) return PSAM_ERR_ARG;
-    if (ep.swiglu && (ep.out_hi || !ep.out_f32 || ep.accumulate || ep.resid || ep.act || (sh.N & 1))) return PSAM_ERR_ARG;
+    if (ep.swiglu && ((!ep.out_hi == !ep.out_f32) || ep.accumulate || ep.resid || ep.act || (sh.N & 1))) return PSAM_ERR_ARG;
     int bn = choose_bn(sh.M, sh.N, sh.K, sh.nb1 * sh.nb2, sh.split_k, o->tile_hint == 1);
     if (o->tile_hint >= 32 && o->tile_hint <= 256 && o->tile_hint % 32 == 0) bn = o->tile_hint;
     if (const char* e = getenv("PSAM_GEMM_BN")) {  // tuning override (tools/gemm_bench.py)

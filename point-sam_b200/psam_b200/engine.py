@@ -20,6 +20,7 @@ from .ops import ACT_GELU, ACT_NONE, ACT_RELU, Split
 
 FUSED_ATTENTION = True
 FUSED_ATTENTION_LONG = os.environ.get("PSAM_FUSED_ATTENTION_LONG", "1") != "0"
+FUSED_INNER_LN = os.environ.get("PSAM_FUSED_INNER_LN", "1") != "0"  # SwiGLU.norm folded into the fc1 / fc2 GEMM epilogues
 FUSED_MASK_DOT = os.environ.get("PSAM_FUSED_MASK_DOT", "1") != "0"
 PASSES = 3  # split-bf16 (fp32-parity) mode; 1 = plain bf16 (fails the 1e-3 parity bound)
 
@@ -171,7 +172,16 @@ class _PackedBlock:
             self.gn, self.bn, self.epsn = gpad, bpad, mlp.norm.eps  # zero-padded to Hp for the float4 LN path
             w2 = torch.zeros((D, Hp), dtype=torch.float32, device=dev)
             w2[:, :Hd] = mlp.fc2.weight.detach().float()
-            self.w2, self.bb2 = ops.pack_weight(w2), _f32(mlp.fc2.bias)
+            self.fold_ln = FUSED_INNER_LN
+            if self.fold_ln:
+                # fc2(LN(h)) = rstd * (h @ (W2 * gamma)^T - mean * (W2 @ gamma)) + (W2 @ beta + b2): the normalisation becomes a
+                # per-row scale / per-column offset in the fc2 epilogue, fed by row sums the fc1 epilogue accumulates
+                w2d = w2.double()
+                self.w2 = ops.pack_weight((w2d * gpad.double()[None, :]).float())
+                self.c2 = (w2d @ gpad.double()).float().contiguous()
+                self.bb2 = (w2d @ bpad.double() + mlp.fc2.bias.detach().double()).float().contiguous()
+            else:
+                self.w2, self.bb2 = ops.pack_weight(w2), _f32(mlp.fc2.bias)
         else:
             self.hid = mlp.fc1.out_features
             self.w1, self.bb1 = ops.pack_weight(mlp.fc1.weight), _f32(mlp.fc1.bias)
@@ -245,7 +255,15 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
         ops.gemm(att, pb.wproj, bias=pb.bproj, out_f32=x, resid=x, passes=PASSES)
     # MLP
     ops.layernorm(x, pb.g2, pb.b2, pb.eps2, out_split=xn)
-    if pb.swiglu:
+    fold = None
+    if pb.swiglu and pb.fold_ln:
+        # h = silu(fc1_g) * fc1_x leaves the fc1 epilogue as split-bf16 together with its row sums; SwiGLU.norm is applied
+        # inside the fc2 epilogue (no LayerNorm kernel, no fp32 copy of h)
+        stats = torch.zeros((M, 2), dtype=torch.float32, device=dev)
+        h = Split(M, pb.hp, dev, pitch=pb.hp)
+        ops.gemm(xn, pb.w1, bias=pb.bb1, out_split=h, passes=PASSES, swiglu=True, stats_out=stats)
+        fold = (stats, pb.c2, pb.hid, pb.epsn)
+    elif pb.swiglu:
         hf = torch.empty((M, pb.hp), dtype=torch.float32, device=dev)
         ops.gemm(xn, pb.w1, bias=pb.bb1, out_f32=hf, passes=PASSES, swiglu=True)  # hf = silu(fc1_g) * fc1_x
         h = Split(M, pb.hp, dev, pitch=pb.hp)  # columns hid..hp are zero-filled by the LayerNorm kernel
@@ -255,9 +273,9 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
         ops.gemm(xn, pb.w1, bias=pb.bb1, out_split=h, act=ACT_GELU, passes=PASSES)
     sk = _split_k_for(M, D, pb.hid)
     if sk > 1:
-        ops.gemm(h, pb.w2, bias=pb.bb2, out_f32=x, accumulate=True, split_k=sk, passes=PASSES)
+        ops.gemm(h, pb.w2, bias=pb.bb2, out_f32=x, accumulate=True, split_k=sk, passes=PASSES, ln_fold=fold)
     else:
-        ops.gemm(h, pb.w2, bias=pb.bb2, out_f32=x, resid=x, passes=PASSES)
+        ops.gemm(h, pb.w2, bias=pb.bb2, out_f32=x, resid=x, passes=PASSES, ln_fold=fold)
 
 
 def run_pc_encoder(enc, coords, features):

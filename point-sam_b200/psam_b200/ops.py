@@ -134,7 +134,8 @@ def gemm_raw(a: Operand, w: Operand, out: GemmOut, passes: int = 3, split_k: int
 def gemm(a: Split, w: Split, *, bias=None, out_f32: Optional[torch.Tensor] = None, out_split: Optional[Split] = None,
          resid: Optional[torch.Tensor] = None, act: int = ACT_NONE, alpha: float = 1.0, accumulate: bool = False,
          split_k: int = 1, passes: int = 3, rows: Optional[int] = None, swiglu: bool = False,
-         gmax: Optional[torch.Tensor] = None, group_rows: int = 0, rowdot=None):
+         gmax: Optional[torch.Tensor] = None, group_rows: int = 0, rowdot=None, stats_out: Optional[torch.Tensor] = None,
+         ln_fold=None):
     """out = act(alpha * a @ w^T + bias (+ resid)); a [M,K], w [N,K] split-bf16."""
     M = rows if rows is not None else a.rows
     o = GemmOut()
@@ -154,6 +155,10 @@ def gemm(a: Split, w: Split, *, bias=None, out_f32: Optional[torch.Tensor] = Non
     if rowdot is not None:  # (w [Z,C,N], out [Z,C,rows] zero-filled)
         rw, ro = rowdot
         o.rd_w, o.rd_out, o.rd_rows, o.rd_c = nv.ptr(rw), nv.ptr(ro), ro.shape[-1], ro.shape[-2]
+    o.stats_out = nv.ptr(stats_out)
+    if ln_fold is not None:  # (stats [M,2], c [N], H, eps): LayerNorm over the K axis folded into this GEMM
+        st, c, hh, eps = ln_fold
+        o.ln_stats, o.ln_c, o.ln_h, o.ln_eps = nv.ptr(st), nv.ptr(c), int(hh), float(eps)
     gemm_raw(a.operand(rows=M), w.operand(), o, passes, split_k)
 
 

@@ -238,6 +238,51 @@ def test_gemm_tc_fused_group_max_and_row_dot():
         ops.gemm(A, W, bias=b, rowdot=(hyper, torch.zeros(Z, C, R + 1, device=_dev())))  # rows not a multiple of 32
 
 
+def test_gemm_tc_swiglu_stats_and_folded_layernorm():
+    """fc2(LayerNorm(silu(g) * x)) with the normalisation folded into the two GEMM epilogues (timm SwiGLU with scale_mlp,
+    as in EVA02) against the unfused fp64 computation."""
+    ops = _ops()
+    M, D, Hd = 300, 256, 683
+    Hp = (Hd + 63) // 64 * 64
+    xin = _rand(M, D, seed=31)
+    wg, wx = _rand(Hd, D, seed=32, scale=D ** -0.5), _rand(Hd, D, seed=33, scale=D ** -0.5)
+    bg, bx = _rand(Hd, seed=34, scale=0.1), _rand(Hd, seed=35, scale=0.1)
+    gamma, beta = 1.0 + 0.2 * _rand(Hd, seed=36), 0.1 * _rand(Hd, seed=37)
+    w2, b2 = _rand(D, Hd, seed=38, scale=Hd ** -0.5), _rand(D, seed=39, scale=0.1)
+    resid = _rand(M, D, seed=40)
+    eps = 1e-6
+    h = torch.nn.functional.silu(xin.double() @ wg.double().t() + bg.double()) * (xin.double() @ wx.double().t() + bx.double())
+    want = resid.double() + torch.nn.functional.layer_norm(h, (Hd,), gamma.double(), beta.double(), eps) @ w2.double().t() + b2.double()
+    # pack as the engine does
+    w1 = torch.zeros(2 * Hp, D, device=_dev())
+    b1 = torch.zeros(2 * Hp, device=_dev())
+    w1[0:2 * Hd:2], w1[1:2 * Hd:2] = wg, wx
+    b1[0:2 * Hd:2], b1[1:2 * Hd:2] = bg, bx
+    gpad, bpad = torch.zeros(Hp, device=_dev()), torch.zeros(Hp, device=_dev())
+    gpad[:Hd], bpad[:Hd] = gamma, beta
+    w2p = torch.zeros(D, Hp, device=_dev())
+    w2p[:, :Hd] = w2
+    W1, W2g = ops.pack_weight(w1), ops.pack_weight((w2p.double() * gpad.double()[None]).float())
+    c2 = (w2p.double() @ gpad.double()).float().contiguous()
+    d2 = (w2p.double() @ bpad.double() + b2.double()).float().contiguous()
+    X = ops.pack_weight(xin)
+    for sk in (1, 3):
+        stats = torch.zeros(M, 2, device=_dev())
+        hs = ops.Split(M, Hp, _dev(), pitch=Hp)
+        ops.gemm(X, W1, bias=b1, out_split=hs, swiglu=True, stats_out=stats)
+        assert float((hs.float()[:, :Hd] - h.float()).abs().max()) < 1e-4
+        assert float(hs.float()[:, Hd:].abs().max()) == 0.0
+        torch.testing.assert_close(stats[:, 0], h.sum(-1).float(), atol=2e-3, rtol=1e-5)
+        torch.testing.assert_close(stats[:, 1], (h * h).sum(-1).float(), atol=2e-3, rtol=1e-5)
+        out = resid.clone()
+        if sk > 1:
+            ops.gemm(hs, W2g, bias=d2, out_f32=out, accumulate=True, split_k=sk, ln_fold=(stats, c2, Hd, eps))
+        else:
+            ops.gemm(hs, W2g, bias=d2, out_f32=out, resid=out, ln_fold=(stats, c2, Hd, eps))
+        err = float((out - want.float()).abs().max())
+        assert err < 1e-4 * max(1.0, float(want.abs().max())), (sk, err)
+
+
 def test_gemm_tc_batched_attention_shapes():
     """The batched operand views used by the ViT attention (heads = b1, clouds = b2)."""
     from psam_b200 import native as nv

@@ -31,8 +31,11 @@ def _report(name, got, want):
           f"range=[{float(want.min()):.3f},{float(want.max()):.3f}]")
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny_fused_qkv"])
-def test_golden_end_to_end(golden_dir, name):
+@pytest.mark.parametrize("name,fold_ln", [("tiny", True), ("tiny_fused_qkv", True), ("tiny", False)])
+def test_golden_end_to_end(golden_dir, name, fold_ln, monkeypatch):
+    from psam_b200 import engine
+
+    monkeypatch.setattr(engine, "FUSED_INNER_LN", fold_ln)  # SwiGLU.norm folded into the GEMM epilogues / separate kernel
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     B, N, G, K, P, seed = [int(v) for v in g["meta"]]
     model, oracle = _build(str(g["encoder"]), G, K, 1234 + seed)
