@@ -51,25 +51,45 @@ def set_group_shape(model, num_points: int):
             g.group_size = 2
 
 
-def evaluate(model, files: Sequence[str], rotation: Optional[np.ndarray] = None, log=print) -> Dict[str, object]:
-    """Returns {"total": [prompt_iters], "per_object": {name: [prompt_iters]}, "object_mean": [prompt_iters]}."""
-    total: List[np.ndarray] = []
-    per_obj: Dict[str, List[np.ndarray]] = {}
+def evaluate(model, files: Sequence[str], rotation: Optional[np.ndarray] = None, log=print, rank: Optional[int] = None,
+             world: Optional[int] = None) -> Dict[str, object]:
+    """Returns {"total": [prompt_iters], "per_object": {name: [prompt_iters]}, "object_mean": [prompt_iters]}.
+
+    Crops are independent, so with several processes (one per GPU, torch.distributed initialised) each rank evaluates a
+    contiguous slice of `files` and the per-crop IoU rows are all-gathered once at the end; every rank
+    returns the same aggregate.  Single process: rank/world default to 0/1."""
+    import torch.distributed as dist
+
+    from psam_b200.parallel import gather_metric, shard_range
+
+    files = list(files)
+    if world is None:
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+    lo, hi = shard_range(len(files), rank or 0, world)
+    rows: List[np.ndarray] = []
     model.eval()
+    dev = next(model.parameters()).device
     with torch.no_grad():
-        for path in files:
-            name = os.path.basename(path).split("_")[0]
-            data = transform_fn(load_crop(path, rotation), device=next(model.parameters()).device)
+        for path in files[lo:hi]:
+            data = transform_fn(load_crop(path, rotation), device=dev)
             set_group_shape(model, data["coords"].shape[1])
             outputs = model(**data, is_eval=True)
             gt = data["gt_masks"].flatten(0, 1)
-            ious = np.array([compute_iou(o["prompt_masks"], gt).detach().cpu().numpy().mean() for o in outputs])
-            per_obj.setdefault(name, []).append(ious)
-            total.append(ious)
+            rows.append(np.array([compute_iou(o["prompt_masks"], gt).detach().cpu().numpy().mean() for o in outputs]))
             if log:
-                log(f"Current mean IoU: {np.array(total).mean(axis=0)}")
+                log(f"[rank {rank or 0}] current mean IoU: {np.array(rows).mean(axis=0)}")
+    iters = int(getattr(model, "prompt_iters", rows[0].shape[0] if rows else 0))
+    local = torch.tensor(np.array(rows), dtype=torch.float32).reshape(len(rows), iters)
+    if world > 1:
+        gdev = dev if dist.get_backend() == "nccl" else torch.device("cpu")
+        local = gather_metric(local.to(gdev), len(files)).cpu()
+    ious = local.numpy()
+    per_obj: Dict[str, List[np.ndarray]] = {}
+    for path, r in zip(files, ious):
+        per_obj.setdefault(os.path.basename(path).split("_")[0], []).append(r)
     per = {k: np.array(v).mean(axis=0) for k, v in per_obj.items()}
-    return {"total": np.array(total).mean(axis=0) if total else np.zeros(0),
+    return {"total": ious.mean(axis=0) if len(ious) else np.zeros(0),
             "per_object": per,
             "object_mean": np.array(list(per.values())).mean(axis=0) if per else np.zeros(0)}
 
@@ -91,10 +111,19 @@ def main(argv=None):
     model.apply(replace_with_fused_layernorm)
     if args.ckpt_path:
         load_model(model, args.ckpt_path)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:  # torchrun: one process per GPU, crops sharded by rank
+        import torch.distributed as dist
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
     model.eval().cuda()
     res = evaluate(model, sorted(glob.glob(args.data)))
-    print(f"Total mean IoU: {res['total']}")
-    print(f"Object mean IoU: {res['object_mean']}")
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"Total mean IoU: {res['total']}")
+        print(f"Object mean IoU: {res['object_mean']}")
+    if world > 1:
+        dist.destroy_process_group()
     return res
 
 

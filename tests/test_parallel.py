@@ -64,3 +64,78 @@ def test_shard_range_properties():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- evaluation driver sharded by crops (host logic only: a stub model stands in for the CUDA path) ----------------
+class _StubGrouper:
+    num_groups, group_size = 0, 0
+
+
+class _StubModel(torch.nn.Module):
+    """Deterministic per-cloud outputs on CPU: iteration t predicts the ground truth shifted by t points."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.zeros(1))
+        self.prompt_iters = 3
+        self.pc_encoder = type("E", (), {"patch_embed": type("P", (), {"grouper": _StubGrouper()})()})()
+
+    def forward(self, coords, features, gt_masks, is_eval=False):
+        gt = gt_masks.flatten(0, 1).float()
+        return [{"prompt_masks": torch.roll(gt, t * 7, dims=1) * 2 - 1} for t in range(self.prompt_iters)]
+
+
+def _write_crops(tmpdir, n):
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(REPO, "point-sam_b200"))
+    from pc_sam.utils import ply
+
+    files = []
+    for i in range(n):
+        r = np.random.default_rng(i)
+        m = 200 + 10 * i
+        files.append(os.path.join(tmpdir, f"{'car' if i % 2 else 'tree'}_{i:03d}.ply"))
+        ply.write_ply(files[-1], {"x": r.normal(size=m).astype(np.float32), "y": r.normal(size=m).astype(np.float32),
+                                  "z": r.normal(size=m).astype(np.float32), "R": r.integers(0, 256, m).astype(np.uint8),
+                                  "G": r.integers(0, 256, m).astype(np.uint8), "B": r.integers(0, 256, m).astype(np.uint8),
+                                  "label": (r.random(m) < 0.4).astype(np.int32)})
+    return files
+
+
+def _eval_worker(rank, world, port, files, q):
+    sys.path.insert(0, os.path.join(REPO, "point-sam_b200"))
+    from evaluation import eval_kitti
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = eval_kitti.evaluate(_StubModel(), files, log=None)
+    q.put((rank, res["total"].tolist(), {k: v.tolist() for k, v in res["per_object"].items()}, res["object_mean"].tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_evaluation_matches_single_process(tmp_path):
+    sys.path.insert(0, os.path.join(REPO, "point-sam_b200"))
+    from evaluation import eval_kitti
+
+    files = _write_crops(str(tmp_path), 5)
+    single = eval_kitti.evaluate(_StubModel(), files, log=None)
+    assert single["total"].shape == (3,) and set(single["per_object"]) == {"car", "tree"}
+    assert abs(single["total"][0] - 1.0) < 1e-6 and single["total"][1] < 1.0  # iteration 0 reproduces the ground truth
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_eval_worker, args=(r, world, port, files, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, total, per, omean in res:
+        assert total == pytest.approx(single["total"].tolist(), abs=1e-6)
+        assert omean == pytest.approx(single["object_mean"].tolist(), abs=1e-6)
+        for k in per:
+            assert per[k] == pytest.approx(single["per_object"][k].tolist(), abs=1e-6)
