@@ -176,3 +176,74 @@ def test_eval_helpers_cpu(tmp_path):
         eval_kitti.set_group_shape(M, n)
         g = M.pc_encoder.patch_embed.grouper
         assert (g.num_groups, g.group_size) == want
+
+
+def test_demo_http_routes_wire_format(tmp_path):
+    """The stdlib HTTP front end of the demo: route names, JSON bodies and error mapping of demo/app.py (a stub session
+    stands in for the CUDA-backed SegmentSession; the session itself is covered by the GPU tests)."""
+    import threading
+    import urllib.error
+    import urllib.request
+    from http.server import ThreadingHTTPServer
+
+    from demo.app import make_handler
+
+    calls = []
+
+    class Stub:
+        def segment(self, req):
+            calls.append(("segment", req))
+            if req.get("prompt_label") == 7:
+                raise ValueError("Input coordinates must be normalized to [-1, 1].")
+            return {"seg": [True, False, True]}
+
+        def sampled_pointcloud(self, req):
+            calls.append(("sampled", sorted(req)))
+            return {"response": "success"}
+
+        def pointcloud(self, path):
+            calls.append(("pointcloud", os.path.basename(path)))
+            return {"xyz": [0.0, 0.0, 0.0], "rgb": [1.0, 1.0, 1.0]}
+
+        def clear(self):
+            return {"status": "cleared"}
+
+        def next(self):
+            return {"status": "cleared"}
+
+        def save(self):
+            return {"status": "saved"}
+
+    static = tmp_path / "static"
+    static.mkdir()
+    (static / "index.html").write_text("<html>ok</html>")
+    srv = ThreadingHTTPServer(("127.0.0.1", 0), make_handler(Stub(), str(static), str(static / "models")))
+    port = srv.server_address[1]
+    t = threading.Thread(target=srv.serve_forever, daemon=True)
+    t.start()
+    try:
+        def post(route, body):
+            req = urllib.request.Request(f"http://127.0.0.1:{port}{route}", data=json.dumps(body).encode(),
+                                         headers={"Content-Type": "application/json"})
+            return json.loads(urllib.request.urlopen(req, timeout=10).read())
+
+        assert post("/segment", {"prompt_point": [0.1, 0.2, 0.3], "prompt_label": 1}) == {"seg": [True, False, True]}
+        assert calls[-1] == ("segment", {"prompt_point": [0.1, 0.2, 0.3], "prompt_label": 1})
+        assert post("/sampled_pointcloud", {"points": {"0": 0.0}, "colors": {"0": 1.0}}) == {"response": "success"}
+        assert post("/clear", {}) == {"status": "cleared"} and post("/next", {}) == {"status": "cleared"}
+        assert post("/save", {}) == {"status": "saved"}
+        got = json.loads(urllib.request.urlopen(f"http://127.0.0.1:{port}/pointcloud/scene.ply", timeout=10).read())
+        assert got == {"xyz": [0.0, 0.0, 0.0], "rgb": [1.0, 1.0, 1.0]} and calls[-1] == ("pointcloud", "scene.ply")
+        assert urllib.request.urlopen(f"http://127.0.0.1:{port}/", timeout=10).read() == b"<html>ok</html>"
+        with pytest.raises(urllib.error.HTTPError) as e:
+            post("/segment", {"prompt_point": [9, 9, 9], "prompt_label": 7})
+        assert e.value.code == 400 and "normalized" in json.loads(e.value.read())["error"]
+        with pytest.raises(urllib.error.HTTPError) as e:
+            post("/nope", {})
+        assert e.value.code == 404
+        with pytest.raises(urllib.error.HTTPError) as e:
+            urllib.request.urlopen(f"http://127.0.0.1:{port}/static/../../etc/passwd", timeout=10)
+        assert e.value.code == 404
+    finally:
+        srv.shutdown()
+        srv.server_close()
