@@ -1,7 +1,8 @@
 """Evaluation driver with the behaviour of /root/reference/evaluation/eval_kitti.py:284-398 on top of the sm_100a
 path: binary PLY crops (fields x y z R G B label) -> normalisation -> per-cloud group-count / group-size override ->
 ``model(**data, is_eval=True)`` (iterative GT-driven prompting) -> IoU per prompt iteration, averaged per object class
-and overall.  The dataset glob and the optional rotation are arguments instead of hard-coded paths."""
+and overall.  The dataset glob is an argument instead of a hard-coded path; every crop is rotated by the reference's
+fixed R.from_euler("xyz", [-90, 180, 0]) unless --rotation says otherwise (the network is not rotation invariant)."""
 from __future__ import annotations
 
 import argparse
@@ -38,6 +39,31 @@ def load_crop(path: str, rotation: Optional[np.ndarray] = None) -> Dict[str, np.
         xyz = np.float32(xyz @ np.asarray(rotation, dtype=np.float64).T)
     rgb = np.column_stack([pc["R"], pc["G"], pc["B"]]).astype(np.float32)
     return {"xyz": xyz, "rgb": rgb, "mask": pc["label"].astype(np.int32)}
+
+
+REFERENCE_EULER_XYZ_DEG = (-90.0, 180.0, 0.0)  # eval_kitti.py:18: r = R.from_euler("xyz", [-90, 180, 0], degrees=True)
+
+
+def euler_xyz_matrix(deg: Sequence[float]) -> np.ndarray:
+    """scipy's Rotation.from_euler("xyz", deg, degrees=True).as_matrix() (extrinsic x, then y, then z), so that
+    ``xyz @ M.T`` equals ``r.apply(xyz)`` of the reference driver (eval_kitti.py:18,347)."""
+    a, b, c = (np.deg2rad(float(v)) for v in deg)
+    rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    return rz @ ry @ rx
+
+
+def parse_rotation(spec: Optional[str]) -> Optional[np.ndarray]:
+    """--rotation: 'reference' (default: the reference driver's -90,180,0), 'none', or 'ax,ay,az' euler xyz in degrees."""
+    if spec is None or spec == "reference":
+        return euler_xyz_matrix(REFERENCE_EULER_XYZ_DEG)
+    if spec.lower() == "none":
+        return None
+    vals = [float(v) for v in spec.split(",")]
+    if len(vals) != 3:
+        raise ValueError("--rotation expects 'reference', 'none' or three comma-separated euler xyz angles in degrees")
+    return euler_xyz_matrix(vals)
 
 
 def set_group_shape(model, num_points: int):
@@ -104,6 +130,8 @@ def main(argv=None):
     ap.add_argument("--config_dir", type=str, default=None, help="the reference's configs/ directory (optional)")
     ap.add_argument("--ckpt_path", type=str, default=None)
     ap.add_argument("--data", type=str, required=True, help="glob of binary PLY crops (x y z R G B label)")
+    ap.add_argument("--rotation", type=str, default="reference",
+                    help="'reference' = euler xyz -90,180,0 deg as eval_kitti.py:18 (default), 'none', or 'ax,ay,az' in degrees")
     args, overrides = ap.parse_known_args(argv)
     cfg = compose(args.config_dir, args.config, overrides)["model"] if args.config_dir else model_config(args.config)
     torch.manual_seed(42)
@@ -118,7 +146,7 @@ def main(argv=None):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
     model.eval().cuda()
-    res = evaluate(model, sorted(glob.glob(args.data)))
+    res = evaluate(model, sorted(glob.glob(args.data)), rotation=parse_rotation(args.rotation))
     if int(os.environ.get("RANK", "0")) == 0:
         print(f"Total mean IoU: {res['total']}")
         print(f"Object mean IoU: {res['object_mean']}")

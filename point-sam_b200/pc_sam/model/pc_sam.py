@@ -135,6 +135,11 @@ class PointCloudSAM(nn.Module):
         sampler (pc_sam/model/common.py:287-474) restated in pc_sam.model.prompt_sampling."""
         from .prompt_sampling import sample_prompts_adapter
 
+        if self.training:
+            # the reference's train() branch (pc_sam.py:150-165: mask-refinement iterations without new prompts, random
+            # prompt sampler, autograd) is not part of this inference-only path; fail instead of silently doing eval
+            raise NotImplementedError("psam_b200 is an inference-only path: call model.eval() (training mode of "
+                                      "PointCloudSAM.forward is not implemented)")
         coords = coords if coords is not None else xyz
         features = features if features is not None else rgb
         gt_masks = gt_masks if gt_masks is not None else mask

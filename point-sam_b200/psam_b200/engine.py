@@ -7,8 +7,10 @@ lazily and cached per module; the cache is keyed on parameter storage/version so
 """
 from __future__ import annotations
 
-import os
+import contextlib
 import math
+import os
+import threading
 from ctypes import byref
 from typing import Optional
 
@@ -138,8 +140,126 @@ def run_knn_grouper(g, xyz, features, use_fps=True):
 # ------------------------------------------------------------------------------------------------
 # timm EVA / EVA02 blocks + PointCloudEncoder, pc_sam/model/pc_encoder.py:84-145
 # ------------------------------------------------------------------------------------------------
+def _is_noop(m) -> bool:
+    """Identity-like sub-module of an inference-only block (None, nn.Identity, Dropout / DropPath with p == 0 or in eval mode)."""
+    if m is None or isinstance(m, torch.nn.Identity):
+        return True
+    p = getattr(m, "p", getattr(m, "drop_prob", None))
+    if p is not None and isinstance(m, torch.nn.Module) and not any(True for _ in m.parameters()):
+        return float(p) == 0.0 or not m.training
+    return False
+
+
+def _refuse(what: str):
+    raise NotImplementedError(
+        f"psam_b200: the transformer block carries {what}, which this engine does not execute - results would be silently "
+        "wrong.  Modelled: timm EvaBlock as Point-SAM calls it (pre-LN, rope=None, no LayerScale, SwiGLU+inner LN or GELU Mlp).")
+
+
+_BLOCK_CHILDREN = {"norm1", "attn", "norm2", "mlp", "drop_path1", "drop_path2"}
+_ATTN_CHILDREN = {"q_proj", "k_proj", "v_proj", "qkv", "proj", "norm", "q_norm", "k_norm", "attn_drop", "proj_drop"}
+_ATTN_PARAMS = {"q_bias", "v_bias", "k_bias"}
+_SWIGLU_CHILDREN = {"fc1_g", "fc1_x", "act", "drop1", "norm", "fc2", "drop2"}
+_MLP_CHILDREN = {"fc1", "act", "drop1", "norm", "fc2", "drop2"}
+
+
+def validate_eva_block(blk) -> None:
+    """Refuse module trees this engine does not model (timm/models/eva.py EvaBlock / EvaAttention options that
+    Point-SAM's released configs leave off): LayerScale (gamma_1/gamma_2), attention inner scale-norm (attn.norm),
+    q/k norms, rotary embedding stored on the module, unknown parameterised children, non-GELU / non-SiLU activations,
+    GluMlp.  Pure Python (no CUDA), unit-tested on CPU with fake modules."""
+    LN = torch.nn.LayerNorm
+    for g in ("gamma_1", "gamma_2"):
+        if getattr(blk, g, None) is not None:
+            _refuse(f"LayerScale ({g})")
+    for n in ("norm1", "norm2"):
+        m = getattr(blk, n, None)
+        if not isinstance(m, LN) or m.weight is None or m.bias is None:
+            _refuse(f"{n} = {type(m).__name__} (expected an affine LayerNorm)")
+    for n in ("drop_path1", "drop_path2"):
+        if not _is_noop(getattr(blk, n, None)):
+            _refuse(f"an active {n}")
+    for name, child in blk.named_children():
+        if name not in _BLOCK_CHILDREN and any(True for _ in child.parameters()):
+            _refuse(f"an unknown parameterised sub-module '{name}'")
+    for name, _ in blk.named_parameters(recurse=False):
+        if name not in ("gamma_1", "gamma_2"):
+            _refuse(f"an unknown block parameter '{name}'")
+    at = getattr(blk, "attn", None)
+    if at is None or not hasattr(at, "num_heads") or getattr(at, "proj", None) is None:
+        _refuse("an attention module without num_heads / proj")
+    for n in ("norm", "q_norm", "k_norm"):
+        if not _is_noop(getattr(at, n, None)):
+            _refuse(f"attn.{n} = {type(getattr(at, n)).__name__} (inner scale-norm / qk-norm)")
+    if getattr(at, "rope", None) is not None:
+        _refuse("a rotary position embedding on attn.rope")
+    for n in ("attn_drop", "proj_drop"):
+        if not _is_noop(getattr(at, n, None)):
+            _refuse(f"an active attn.{n}")
+    for name, child in at.named_children():
+        if name not in _ATTN_CHILDREN and any(True for _ in child.parameters()):
+            _refuse(f"an unknown parameterised sub-module 'attn.{name}'")
+    for name, _ in at.named_parameters(recurse=False):
+        if name not in _ATTN_PARAMS:
+            _refuse(f"an unknown attention parameter 'attn.{name}'")
+    fused = getattr(at, "qkv", None) is not None
+    if fused:
+        if getattr(at.qkv, "bias", None) is not None:
+            _refuse("attn.qkv with its own bias (timm keeps the q/v bias in q_bias / v_bias)")
+        if (getattr(at, "q_bias", None) is None) != (getattr(at, "v_bias", None) is None):
+            _refuse("attn.q_bias without attn.v_bias")
+    else:
+        for n in ("q_proj", "k_proj", "v_proj"):
+            if getattr(at, n, None) is None:
+                _refuse(f"neither attn.qkv nor attn.{n}")
+    mlp = getattr(blk, "mlp", None)
+    if hasattr(mlp, "fc1_g") and hasattr(mlp, "fc1_x"):
+        allowed = _SWIGLU_CHILDREN
+        nm = getattr(mlp, "norm", None)
+        if not isinstance(nm, LN) or nm.weight is None or nm.bias is None:
+            _refuse(f"SwiGLU.norm = {type(nm).__name__} (expected the affine inner LayerNorm of scale_mlp=True)")
+        act = getattr(mlp, "act", None)
+        if act is not None and not isinstance(act, torch.nn.SiLU):
+            _refuse(f"SwiGLU activation {type(act).__name__} (expected SiLU)")
+    elif hasattr(mlp, "fc1") and hasattr(mlp, "fc2"):
+        allowed = _MLP_CHILDREN
+        if mlp.fc1.out_features != mlp.fc2.in_features:
+            _refuse("a gated GluMlp (fc1 twice as wide as fc2's input)")
+        if not _is_noop(getattr(mlp, "norm", None)):
+            _refuse(f"Mlp.norm = {type(mlp.norm).__name__}")
+        act = getattr(mlp, "act", None)
+        if act is not None and not (isinstance(act, torch.nn.GELU) and getattr(act, "approximate", "none") == "none"):
+            _refuse(f"Mlp activation {act!r} (expected exact-erf GELU)")
+    else:
+        _refuse(f"an MLP of type {type(mlp).__name__}")
+    for name, child in mlp.named_children():
+        if name not in allowed and any(True for _ in child.parameters()):
+            _refuse(f"an unknown parameterised sub-module 'mlp.{name}'")
+    for n in ("drop1", "drop2"):
+        if not _is_noop(getattr(mlp, n, None)):
+            _refuse(f"an active mlp.{n}")
+
+
+def validate_transformer(tr) -> list:
+    """pc_encoder.py:136-142 applies pos_drop, blocks, norm, fc_norm.  Returns the LayerNorms to run after the blocks
+    (timm: exactly one of norm / fc_norm is a LayerNorm, the other nn.Identity)."""
+    if not _is_noop(getattr(tr, "pos_drop", None)):
+        _refuse("an active pos_drop")
+    tail = []
+    for n in ("norm", "fc_norm"):
+        m = getattr(tr, n, None)
+        if isinstance(m, torch.nn.LayerNorm) and m.weight is not None and m.bias is not None:
+            tail.append(m)
+        elif not _is_noop(m):
+            _refuse(f"transformer.{n} = {type(m).__name__}")
+    for blk in tr.blocks:
+        validate_eva_block(blk)
+    return tail
+
+
 class _PackedBlock:
     def __init__(self, blk, D):
+        validate_eva_block(blk)
         at = blk.attn
         self.H, self.dh = at.num_heads, D // at.num_heads
         self.g1, self.b1, self.eps1 = _f32(blk.norm1.weight), _f32(blk.norm1.bias), blk.norm1.eps
@@ -148,10 +268,13 @@ class _PackedBlock:
         zeros = torch.zeros(D, dtype=torch.float32, device=dev)
         if getattr(at, "qkv", None) is not None:
             wqkv = at.qkv.weight.detach().float()
-            bqkv = torch.cat([at.q_bias.detach().float(), zeros, at.v_bias.detach().float()])
+            qb = at.q_bias.detach().float() if getattr(at, "q_bias", None) is not None else zeros
+            vb = at.v_bias.detach().float() if getattr(at, "v_bias", None) is not None else zeros
+            bqkv = torch.cat([qb, zeros, vb])
         else:
             wqkv = torch.cat([at.q_proj.weight, at.k_proj.weight, at.v_proj.weight]).detach().float()
-            bqkv = torch.cat([at.q_proj.bias.detach().float(), zeros, at.v_proj.bias.detach().float()])
+            bias = lambda lin: lin.bias.detach().float() if lin.bias is not None else zeros
+            bqkv = torch.cat([bias(at.q_proj), bias(at.k_proj), bias(at.v_proj)])
         self.wqkv, self.bqkv = ops.pack_weight(wqkv), bqkv.contiguous()
         self.wproj, self.bproj = ops.pack_weight(at.proj.weight), _f32(at.proj.bias)
         mlp = blk.mlp
@@ -195,9 +318,8 @@ class _PackedEncoder:
         self.wpp, self.bpp = ops.pack_weight(enc.patch_proj.weight), _f32(enc.patch_proj.bias)
         self.wpos0, self.bpos0 = _f32(enc.pos_embed[0].weight), _f32(enc.pos_embed[0].bias)
         self.wpos2, self.bpos2 = ops.pack_weight(enc.pos_embed[2].weight), _f32(enc.pos_embed[2].bias)
+        self.tail = [(_f32(m.weight), _f32(m.bias), m.eps) for m in validate_transformer(enc.transformer)]
         self.blocks = [_PackedBlock(b, D) for b in enc.transformer.blocks]
-        fn = enc.transformer.fc_norm
-        self.gf, self.bf, self.epsf = _f32(fn.weight), _f32(fn.bias), fn.eps
         self.wout, self.bout = ops.pack_weight(enc.out_proj.weight), _f32(enc.out_proj.bias)
 
 
@@ -294,7 +416,13 @@ def run_pc_encoder(enc, coords, features):
     for pb in pk.blocks:
         _run_block(pb, x, B, L, D)
     xn = Split(M, D, dev)
-    ops.layernorm(x, pk.gf, pk.bf, pk.epsf, out_split=xn)
+    for i, (g_, b_, e_) in enumerate(pk.tail):  # transformer.norm / transformer.fc_norm (pc_encoder.py:141-142)
+        if i + 1 < len(pk.tail):
+            ops.layernorm(x, g_, b_, e_, out_f32=x)
+        else:
+            ops.layernorm(x, g_, b_, e_, out_split=xn)
+    if not pk.tail:
+        ops.split_f32(x, xn)
     out = torch.empty((B, L, enc.embed_dim), dtype=torch.float32, device=dev)
     ops.gemm(xn, pk.wout, bias=pk.bout, out_f32=out.view(M, -1), passes=PASSES)
     return out, patches
@@ -304,9 +432,26 @@ def run_pc_encoder(enc, coords, features):
 # prompt encoders, pc_sam/model/prompt_encoder.py:13-133
 # ------------------------------------------------------------------------------------------------
 _bad_flags = {}
+_flag_ctx = threading.local()
+
+
+@contextlib.contextmanager
+def flag_scope(range_flag: Optional[torch.Tensor] = None, sampler: Optional[torch.Tensor] = None):
+    """Route the device-side error flags of everything run inside the scope to caller-owned tensors.  The graph
+    predictors give every lane its own flags (captured into its CUDA graph), so a bad request is reported for that
+    ticket only and never leaks into an unrelated eager call on the same GPU."""
+    prev = (getattr(_flag_ctx, "range", None), getattr(_flag_ctx, "sampler", None))
+    _flag_ctx.range, _flag_ctx.sampler = range_flag, sampler
+    try:
+        yield
+    finally:
+        _flag_ctx.range, _flag_ctx.sampler = prev
 
 
 def bad_flag(device) -> torch.Tensor:
+    o = getattr(_flag_ctx, "range", None)
+    if o is not None:
+        return o
     f = _bad_flags.get(device)
     if f is None:
         f = torch.zeros(1, dtype=torch.int32, device=device)
@@ -329,6 +474,9 @@ _sampler_flags = {}
 
 def sampler_flag(device) -> torch.Tensor:
     """Sticky device flag set by psam_border_prompt_f32 when a mask has no border to sample from."""
+    o = getattr(_flag_ctx, "sampler", None)
+    if o is not None:
+        return o
     f = _sampler_flags.get(device)
     if f is None:
         f = torch.zeros(1, dtype=torch.int32, device=device)

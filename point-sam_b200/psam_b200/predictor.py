@@ -24,8 +24,16 @@ class GraphPredictor:
         self.masks = self.iou = None
         self.launches_per_step = 0
         self.stream = torch.cuda.Stream(device=d)
+        # this lane's own out-of-range flag (PositionEmbeddingRandom's ValueError, prompt_encoder.py:44-46): written by the
+        # kernels captured in this lane's graph, read back with the result, never shared with other lanes / eager calls
+        self.flag = torch.zeros(1, dtype=torch.int32, device=d)
+        self.flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
 
     def _run(self):
+        with engine.flag_scope(range_flag=self.flag):
+            return self._run_inner()
+
+    def _run_inner(self):
         import os
 
         only = os.environ.get("PSAM_PROFILE_STAGE")  # attribution experiments only (tools/stage_attribution.sh)
@@ -53,28 +61,50 @@ class GraphPredictor:
                 self.masks, self.iou = self._run()
                 self.launches_per_step = nv.LAUNCHES[0] - n0
             self.stream.synchronize()
-            engine.raise_if_out_of_range(self.dev)
+            with engine.flag_scope(range_flag=self.flag):
+                engine.raise_if_out_of_range(self.dev)
             if self.use_graph:
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph, stream=self.stream):
                     self.masks, self.iou = self._run()
         self.stream.synchronize()
 
-    def _load(self, xyz, feats, pc, pl):
+    def _load(self, xyz, feats, pc, pl, caller=None):
+        """Copies run on the predictor's stream.  Device inputs may have been produced on the caller's stream (GPU
+        preprocessing): order this stream behind it.  Pinned host inputs must stay unmodified until the step's result has
+        been read (PipelinedPredictor.wait_lane_free)."""
+        if caller is not None and caller != self.stream and any(t.is_cuda for t in (xyz, feats, pc, pl)):
+            self.stream.wait_stream(caller)
         self.xyz.copy_(xyz, non_blocking=True)
         self.feats.copy_(feats, non_blocking=True)
         self.pc.copy_(pc, non_blocking=True)
         self.pl.copy_(pl, non_blocking=True)
 
     def __call__(self, xyz, feats, pc, pl):
-        """Enqueue one step on the predictor's stream; returns device tensors (valid after stream sync)."""
+        """Enqueue one step on the predictor's stream; returns device tensors (valid after ``check()`` / a stream sync)."""
+        caller = torch.cuda.current_stream(self.dev)
         with torch.no_grad(), torch.cuda.stream(self.stream):
-            self._load(xyz, feats, pc, pl)
+            self._load(xyz, feats, pc, pl, caller)
             if self.graph is not None:
                 self.graph.replay()
             else:
                 self.masks, self.iou = self._run()
+            # the flag travels with the result (4 bytes) and is cleared on-stream for the lane's next step
+            self.flag_host.copy_(self.flag, non_blocking=True)
+            self.flag.zero_()
         return self.masks, self.iou
+
+    def raise_if_flagged(self):
+        """Call after the step's completion has been observed (event / stream sync)."""
+        if int(self.flag_host[0]) != 0:
+            self.flag_host[0] = 0
+            raise ValueError("Input coordinates must be normalized to [-1, 1].")
+
+    def check(self):
+        """Wait for the enqueued step and raise the reference's ValueError (prompt_encoder.py:44-46) if its coordinates
+        or prompts were outside [-1, 1]."""
+        self.stream.synchronize()
+        self.raise_if_flagged()
 
 
 class IterativeGraphPredictor:
@@ -96,11 +126,16 @@ class IterativeGraphPredictor:
         self.outputs = None
         self.launches_per_step = 0
         self.stream = torch.cuda.Stream(device=d)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=d)      # coordinates outside [-1, 1]
+        self.sflag = torch.zeros(1, dtype=torch.int32, device=d)     # a ground-truth mask without border
 
     def _run(self):
-        return self.model(self.xyz, self.feats, self.gt, is_eval=True)
+        with engine.flag_scope(range_flag=self.flag, sampler=self.sflag):
+            return self.model(self.xyz, self.feats, self.gt, is_eval=True)
 
-    def _load(self, xyz, feats, gt):
+    def _load(self, xyz, feats, gt, caller=None):
+        if caller is not None and caller != self.stream and any(t.is_cuda for t in (xyz, feats, gt)):
+            self.stream.wait_stream(caller)
         self.xyz.copy_(xyz, non_blocking=True)
         self.feats.copy_(feats, non_blocking=True)
         self.gt.copy_(gt, non_blocking=True)
@@ -120,8 +155,9 @@ class IterativeGraphPredictor:
         self.stream.synchronize()
 
     def __call__(self, xyz, feats, gt, check: bool = True):
+        caller = torch.cuda.current_stream(self.dev)
         with torch.no_grad(), torch.cuda.stream(self.stream):
-            self._load(xyz, feats, gt)
+            self._load(xyz, feats, gt, caller)
             if self.graph is not None:
                 self.graph.replay()
             else:
@@ -133,8 +169,9 @@ class IterativeGraphPredictor:
     def check(self):
         """One host read for the whole loop: coordinates out of [-1, 1] (ValueError) / masks without a border (RuntimeError)."""
         self.stream.synchronize()
-        engine.raise_if_out_of_range(self.dev)
-        engine.raise_if_sampler_failed(self.dev)
+        with engine.flag_scope(range_flag=self.flag, sampler=self.sflag):
+            engine.raise_if_out_of_range(self.dev)
+            engine.raise_if_sampler_failed(self.dev)
 
 
 class PipelinedPredictor:
@@ -188,8 +225,11 @@ class PipelinedPredictor:
         return self.count - 1
 
     def result(self, ticket: int, to_host: bool = False):
+        """Wait for that cloud only; raises ValueError for THIS ticket if its coordinates / prompts were outside [-1, 1]
+        (the reference raises inside PositionEmbeddingRandom.forward, prompt_encoder.py:44-46)."""
         i = ticket % self.depth
         self.events[i].synchronize()
+        self.lanes[i].raise_if_flagged()
         return self.host_out[i] if to_host else (self.lanes[i].masks, self.lanes[i].iou)
 
     def wait_lane_free(self, ticket: int):

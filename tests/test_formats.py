@@ -247,3 +247,41 @@ def test_demo_http_routes_wire_format(tmp_path):
     finally:
         srv.shutdown()
         srv.server_close()
+
+
+def test_eval_driver_rotation_matches_reference_scipy_rotation(tmp_path):
+    """ADVICE r1: the reference driver rotates every crop by R.from_euler('xyz', [-90, 180, 0]) (eval_kitti.py:18,347);
+    the default of this driver must be that rotation, bit-compatible with scipy's r.apply up to float32 rounding."""
+    from scipy.spatial.transform import Rotation as R
+
+    from evaluation import eval_kitti
+    from pc_sam.utils import ply
+
+    rng = np.random.default_rng(0)
+    xyz = rng.normal(size=(257, 3)).astype(np.float32) * 11
+    for deg in ((-90, 180, 0), (10, -20, 33.5)):
+        want = R.from_euler("xyz", list(deg), degrees=True)
+        np.testing.assert_allclose(eval_kitti.euler_xyz_matrix(deg), want.as_matrix(), atol=1e-12)
+    assert eval_kitti.parse_rotation("none") is None
+    np.testing.assert_allclose(eval_kitti.parse_rotation(None), eval_kitti.parse_rotation("reference"))
+    np.testing.assert_allclose(eval_kitti.parse_rotation("-90,180,0"), eval_kitti.parse_rotation("reference"), atol=1e-15)
+    f = str(tmp_path / "car_0000.ply")
+    ply.write_ply(f, {"x": xyz[:, 0].copy(), "y": xyz[:, 1].copy(), "z": xyz[:, 2].copy(),
+                      "R": np.zeros(257, np.uint8), "G": np.zeros(257, np.uint8), "B": np.zeros(257, np.uint8),
+                      "label": np.ones(257, np.int32)})
+    got = eval_kitti.load_crop(f, eval_kitti.parse_rotation("reference"))["xyz"]
+    want = np.float32(R.from_euler("xyz", [-90, 180, 0], degrees=True).apply(xyz))
+    np.testing.assert_allclose(got, want, atol=2e-6, rtol=0)
+    assert np.array_equal(eval_kitti.load_crop(f, None)["xyz"], xyz)
+
+
+def test_forward_in_training_mode_is_refused():
+    """the inference-only path must not silently run the eval loop when the module is in train() mode."""
+    import pytest
+    import torch
+
+    from pc_sam.model import build_point_sam
+
+    m = build_point_sam("eva02_test_tiny", 8, 4).train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 16, 3), torch.zeros(1, 16, 3), torch.zeros(1, 1, 16, dtype=torch.bool))

@@ -80,6 +80,25 @@ def test_fps_against_reference_cuda_kernel():
         assert (tokenizer_ref.fps(xyz.numpy(), G) == want.numpy()).all(), "oracle vs reference kernel"
 
 
+@pytest.mark.parametrize("N,G,kind", [(200000, 48, "ball"), (200000, 40, "grid"), (524288, 40, "ball"), (524288, 24, "grid")])
+def test_fps_streaming_plan_beyond_cluster_registers(N, G, kind):
+    """N > 131072 no longer fits the 16-CTA register plan: the multi-cluster / streaming plan must reproduce the reference
+    kernel (sample_farthest_points_kernel.cu:8-104: fmaf chain + bit-reversed tie-break) bit for bit, against the C
+    oracle and - when oracle/_ref travelled - against the reference's own kernel compiled for sm_100a."""
+    from oracle import build_ref
+
+    ops = _ops()
+    xyz, _ = synth.make_batch(1, N, 13, kind)
+    x = xyz.to(_dev())
+    got, centers = ops.fps(x, G)
+    want = tokenizer_ref.fps(xyz.numpy(), G)
+    assert np.array_equal(got.cpu().numpy(), want), f"first mismatch at {np.nonzero(got.cpu().numpy() != want)[1][:3]}"
+    assert torch.equal(centers.cpu(), torch.gather(xyz, 1, torch.from_numpy(want)[..., None].expand(-1, -1, 3)))
+    ref = build_ref.load_ref()
+    if ref is not None:
+        assert torch.equal(ref.sample_farthest_points_cuda(x, G).cpu(), got.cpu())
+
+
 # ------------------------------------------------------------------------------------------------
 # kNN / grouping / interpolation
 # ------------------------------------------------------------------------------------------------
