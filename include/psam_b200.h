@@ -125,6 +125,10 @@ typedef struct {
     const float* ln_c;
     int ln_h;
     float ln_eps;
+    int variant;            /* 0 = policy default.  Experiment switches (the library reads no environment variable):
+                             * 0x1 cta_group::2 pairs, 0x2 BK=32 4-stage ring, 0x4 scalar epilogue, 0x8 force / 0x10 forbid the
+                             * dual-resident wide-tile kernel (two 97 KB CTAs per SM; default under tile_hint == 1),
+                             * bits 8-11 W-tile multicast cluster size (2|4), bits 12-15 L2 prefetch depth in k-blocks */
 } psam_gemm_out;
 
 /* C[M,N] = A[M,K] * W[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
@@ -134,14 +138,23 @@ typedef struct {
 int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, const psam_gemm_out* out, int passes, int split_k,
                      cudaStream_t stream);
 
-/* Fused encoder self-attention on tensor cores: out = softmax(Q K^T * scale) V per (cloud, head); exact two-pass
- * softmax with S resident in tensor memory.  q/k/v are split-bf16 operand views [L rows x dh] with nb1 = heads,
- * nb2 = clouds (typically three column windows of the fused qkv activation).  Supports dh == 64 and L <= 512
- * (returns PSAM_ERR_UNSUPPORTED otherwise - the caller then uses psam_gemm_bf16x3 + psam_softmax_split).
+/* Fused encoder self-attention on tensor cores: out = softmax(Q K^T * scale) V per (cloud, head).
+ * q/k/v are split-bf16 operand views [L rows x dh] with nb1 = heads, nb2 = clouds (typically three column windows of
+ * the fused qkv activation).  dh == 64, any L >= 1 (PSAM_ERR_UNSUPPORTED otherwise - the caller then uses
+ * psam_gemm_bf16x3 + psam_softmax_split).  Key blocks are streamed once: S_j lands in a ring of tensor-memory slots,
+ * P_j = exp2(S_j c - m_ref) is written back into the slot as split-bf16 and consumed as the TMEM A operand of the PV
+ * MMA; the reference maximum is moved (and O rescaled) only when a block exceeds it by more than 2^8.
  * Replaces F.scaled_dot_product_attention in timm EvaAttention (blocks called at pc_encoder.py:138-139). */
 int psam_attention_bf16x3(const psam_operand* q, const psam_operand* k, const psam_operand* v, void* out_hi,
                           long long out_plane, long long ldo, long long out_head_stride, long long out_cloud_stride,
                           float scale, cudaStream_t stream);
+
+/* Same contract, computed by the first-generation kernels (exact two-pass softmax with S resident in tensor memory for
+ * L <= 512, two-sweep ring for longer rows, P staged through shared memory).  Kept as an independent implementation
+ * the tests cross-check the streaming kernel against. */
+int psam_attention_bf16x3_twopass(const psam_operand* q, const psam_operand* k, const psam_operand* v, void* out_hi,
+                                  long long out_plane, long long ldo, long long out_head_stride,
+                                  long long out_cloud_stride, float scale, cudaStream_t stream);
 
 /* Small fp32 SIMT linear for the prompt decoder (rows < one MMA tile):
  * Y[z][M,N] = act((X[z] (+X2[z]))[M,K] * W[z][N,K]^T + b[z]) (+R[z]); strides in elements; any pointer

@@ -1,40 +1,11 @@
-"""Deterministic synthetic inputs.  Shared by tests, bench.py and the
-golden-vector generator; pure CPU torch so that every box produces identical tensors."""
-from __future__ import annotations
+"""Deterministic synthetic inputs.  The generator lives with the product package
+(psam_b200/synth.py) so that bench.py's repo arm never imports anything under oracle/; the oracle-side tests and the
+golden-vector generator use it through this re-export."""
+import os
+import sys
 
-import torch
+_PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "point-sam_b200")
+if _PKG not in sys.path:
+    sys.path.insert(0, _PKG)
 
-
-def make_cloud(n: int, seed: int = 0, cloud_id: int = 0, kind: str = "ball"):
-    """xyz [n,3] uniform in the unit ball then reference-normalised (eval_kitti.py:82-88),
-    features [n,3] in [-1,1]."""
-    g = torch.Generator().manual_seed(seed + cloud_id)
-    d = torch.randn(n, 3, generator=g)
-    d = d / d.norm(dim=1, keepdim=True)
-    r = torch.rand(n, generator=g) ** (1.0 / 3.0)
-    xyz = d * r[:, None]
-    if kind == "kitti":
-        xyz = xyz * torch.tensor([1.0, 1.0, 0.15])
-        k = int(0.4 * n)
-        xyz[:k, 2] = xyz[:, 2].min()
-    elif kind == "grid":  # tie-heavy: quantised to a 1/64 grid with duplicated points
-        xyz = torch.round(xyz * 16) / 16
-        xyz[n // 2:] = xyz[: n - n // 2].clone()
-    xyz = xyz - xyz.mean(dim=0, keepdim=True)
-    xyz = xyz / xyz.norm(dim=1).max()
-    feats = torch.rand(n, 3, generator=g) * 2 - 1
-    return xyz.float().contiguous(), feats.float().contiguous()
-
-
-def make_batch(b: int, n: int, seed: int = 0, kind: str = "ball"):
-    xs, fs = zip(*[make_cloud(n, seed, i, kind) for i in range(b)])
-    return torch.stack(xs), torch.stack(fs)
-
-
-def make_prompts(xyz: torch.Tensor, num_prompts: int, seed: int = 0):
-    """prompt p of cloud b = xyz[b, (seed*7919 + 104729*p) mod N]; labels 1,0,1,0..."""
-    B, N, _ = xyz.shape
-    idx = torch.tensor([(seed * 7919 + 104729 * p) % N for p in range(num_prompts)])
-    coords = xyz[:, idx]
-    labels = torch.tensor([1 - (p % 2) for p in range(num_prompts)]).expand(B, -1).contiguous()
-    return coords.contiguous(), labels
+from psam_b200.synth import make_batch, make_cloud, make_prompts, make_region_masks  # noqa: E402,F401

@@ -549,7 +549,369 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// attention_flow_kernel: the production path for dh = 64 at ANY sequence length.
+//
+// The two kernels above run the softmax as two exact sweeps (row maximum first), which serialises the tensor pipe
+// behind the softmax warps (23 % tensor-pipe activity at L = 512, profiles/r01_attention_tc_kernel_ncu_full.md) or
+// recomputes Q K^T (long rows).  This kernel streams the key blocks ONCE:
+//   * S_j = Q K_j^T (split-bf16, 3 passes) lands in one of three 128-column TMEM slots; the MMA warp runs up to
+//     three blocks ahead of the softmax warps (S_0 S_1 S_2 | PV_0 S_3 | PV_1 S_4 | ...).
+//   * softmax warps (2 threads per query row, 64 keys each): S_j -> registers, block maximum (FMNMX3), one named-
+//     barrier exchange between the two threads of a row, P_j = exp2(S_j c - m_ref) with packed fp32x2 arithmetic
+//     (FFMA2 / FADD2), split into bf16 hi / lo and written BACK INTO THE SAME TMEM SLOT (hi in columns [0,64), lo in
+//     [64,128) of the slot, two keys per 32-bit column).  O += P_j V_j then takes P as the TMEM A operand of
+//     tcgen05.mma (V^T is the MN-major smem B operand as before): no shared-memory round trip for P, no proxy fence,
+//     and the freed 64 KB of shared memory hold a 5-deep K/V stage ring.
+//   * the running reference maximum m_ref is only moved when a block maximum exceeds it by more than 2^ATT_TAU
+//     (softmax is shift invariant, P <= 2^ATT_TAU keeps full fp32 / split-bf16 relative precision).  When it moves,
+//     the warps of the affected rows rescale O in TMEM (tcgen05.ld -> mul -> tcgen05.st) after PV_{j-1} has retired -
+//     a rare slow path (never taken when the first block already holds a near-maximal logit).
+// Exactness: the result equals softmax(QK^T c) V up to fp32 rounding (same split-bf16 operands as the other kernels).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int AF_STAGES = 5;
+constexpr int AF_SLOTS = 3;
+constexpr float AF_TAU = 8.0f;  // log2 units
+constexpr int AF_SMEM_TOTAL = ATT_SMEM_Q + AF_STAGES * ATT_SMEM_STAGE + 2 * 2 * 128 * 4 /*row exchange, double buffered*/ + 1024;
+
+// D[tmem] (+)= A[tmem] * B[smem desc]: P is read from tensor memory (row = lane, two bf16 per 32-bit column along K)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+          "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+          "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)),
+        "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
+__device__ __forceinline__ float ex2f(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+    return e;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_flow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                      const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+    pdl_launch_dependents();
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t q_full, pv_done;
+    __shared__ __align__(8) uint64_t kv_full[AF_STAGES], kv_empty[AF_STAGES];
+    __shared__ __align__(8) uint64_t s_full[AF_SLOTS], p_full[AF_SLOTS];
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t sQ = smem_base;
+    const uint32_t sKV = sQ + ATT_SMEM_Q;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int nkb = (p.L + ATT_BKEY - 1) / ATT_BKEY;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+        mbar_init(smem_u32(&q_full), 1);
+        mbar_init(smem_u32(&pv_done), 1);
+        for (int s = 0; s < AF_STAGES; ++s) {
+            mbar_init(smem_u32(&kv_full[s]), 1);
+            mbar_init(smem_u32(&kv_empty[s]), 1);
+        }
+        for (int s = 0; s < AF_SLOTS; ++s) {
+            mbar_init(smem_u32(&s_full[s]), 1);
+            mbar_init(smem_u32(&p_full[s]), 256);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const uint32_t t_o = tmem_base;          // O: columns [0, 64)
+    const uint32_t t_s = tmem_base + 64u;    // slot s: columns [64 + 128 s, 64 + 128 s + 128)
+    pdl_wait();
+
+    // Operand blocks travel through the stage ring in the order the MMA warp consumes them:
+    //   K_0 K_1 K_2 | V_0 K_3 | V_1 K_4 | ... | V_{nkb-1}
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t qb = smem_u32(&q_full);
+            mbar_arrive_expect_tx(qb, ATT_SMEM_Q);
+            tma_load_5d(sQ, &tmap_q, qb, 0, q_tile * ATT_BQ, 0, h, b);
+            int i = 0;
+            auto load = [&](const CUtensorMap* tm, int blk) {
+                const int s = i % AF_STAGES;
+                mbar_wait(smem_u32(&kv_empty[s]), ((uint32_t)(i / AF_STAGES) & 1u) ^ 1u);
+                const uint32_t fb = smem_u32(&kv_full[s]);
+                mbar_arrive_expect_tx(fb, ATT_SMEM_STAGE);
+                tma_load_5d(sKV + s * ATT_SMEM_STAGE, tm, fb, 0, blk * ATT_BKEY, 0, h, b);
+                ++i;
+            };
+            for (int j = 0; j < AF_SLOTS && j < nkb; ++j) load(&tmap_k, j);
+            for (int j = 0; j < nkb; ++j) {
+                load(&tmap_v, j);
+                if (j + AF_SLOTS < nkb) load(&tmap_k, j + AF_SLOTS);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, ATT_BKEY);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_DH) | (1u << 16);  // B (V) MN-major; A (P) from TMEM, K-major
+        mbar_wait(smem_u32(&q_full), 0);
+        tc_fence_after();
+        const uint64_t q_hi = umma_desc_k_sw128(sQ), q_lo = umma_desc_k_sw128(sQ + ATT_TILE);
+        int i = 0;
+        auto issue_s = [&](int g) {
+            const int s = i % AF_STAGES, slot = g % AF_SLOTS;
+            mbar_wait(smem_u32(&kv_full[s]), (uint32_t)(i / AF_STAGES) & 1u);
+            tc_fence_after();
+            if (lane == 0) {
+                // slot reuse needs no barrier: S_g is issued after PV_{g-3}, which was issued after P_{g-3} was complete
+                // (softmax done with S_{g-3}) and reads P_{g-3} before this MMA writes (tcgen05.mma executes in issue order)
+                const uint32_t sk = sKV + s * ATT_SMEM_STAGE;
+                const uint64_t k_hi = umma_desc_k_sw128(sk), k_lo = umma_desc_k_sw128(sk + ATT_TILE);
+                const uint32_t d_s = t_s + (uint32_t)(slot * ATT_BKEY);
+#pragma unroll
+                for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_hi + 2 * k, k_hi + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_lo + 2 * k, k_hi + 2 * k, idesc_s, 1u);
+#pragma unroll
+                for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_hi + 2 * k, k_lo + 2 * k, idesc_s, 1u);
+                umma_commit(smem_u32(&kv_empty[s]));
+                umma_commit(smem_u32(&s_full[slot]));
+            }
+            __syncwarp();
+            ++i;
+        };
+        for (int g = 0; g < AF_SLOTS && g < nkb; ++g) issue_s(g);
+        for (int j = 0; j < nkb; ++j) {
+            const int s = i % AF_STAGES, slot = j % AF_SLOTS;
+            mbar_wait(smem_u32(&kv_full[s]), (uint32_t)(i / AF_STAGES) & 1u);
+            mbar_wait(smem_u32(&p_full[slot]), (uint32_t)(j / AF_SLOTS) & 1u);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sv = sKV + s * ATT_SMEM_STAGE;
+                const uint64_t v_hi = umma_desc_mn_sw128(sv), v_lo = umma_desc_mn_sw128(sv + ATT_TILE);
+                const uint32_t a_hi = t_s + (uint32_t)(slot * ATT_BKEY), a_lo = a_hi + 64u;
+#pragma unroll
+                for (int ks = 0; ks < ATT_BKEY / 16; ++ks)  // 16 keys = 8 TMEM columns of P, 16 rows (2048 B) of V
+                    umma_bf16_ts(t_o, a_hi + ks * 8, v_hi + (uint64_t)(ks * (2048 >> 4)), idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < ATT_BKEY / 16; ++ks)
+                    umma_bf16_ts(t_o, a_lo + ks * 8, v_hi + (uint64_t)(ks * (2048 >> 4)), idesc_o, 1u);
+#pragma unroll
+                for (int ks = 0; ks < ATT_BKEY / 16; ++ks)
+                    umma_bf16_ts(t_o, a_hi + ks * 8, v_lo + (uint64_t)(ks * (2048 >> 4)), idesc_o, 1u);
+                umma_commit(smem_u32(&kv_empty[s]));
+                umma_commit(smem_u32(&pv_done));
+            }
+            __syncwarp();
+            ++i;
+            if (j + AF_SLOTS < nkb) issue_s(j + AF_SLOTS);
+        }
+    } else {
+        // ===================== softmax / correction / epilogue warps =====================
+        const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+        const int sub = (warp - 2) >> 2;          // 0/1: which 64 keys of every 128-key block this thread owns
+        const int r = quarter * 32 + lane;        // row inside the tile == TMEM lane
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        float* xchg = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn)) + ATT_SMEM_Q + AF_STAGES * ATT_SMEM_STAGE);
+        const float c = p.scale_log2e;
+        float mref = 0.f;                          // reference maximum of the raw logits (set by block 0)
+        float2 lsum2 = make_float2(0.f, 0.f);
+        for (int j = 0; j < nkb; ++j) {
+            const int slot = j % AF_SLOTS;
+            mbar_wait(smem_u32(&s_full[slot]), (uint32_t)(j / AF_SLOTS) & 1u);
+            tc_fence_after();
+            const uint32_t t_slot = t_s + lane_off + (uint32_t)(slot * ATT_BKEY);
+            uint32_t v[64];
+            {
+                uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
+                uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
+                tmem_ld_32x32(t_slot + (uint32_t)(sub * 64), v0);
+                tmem_ld_32x32(t_slot + (uint32_t)(sub * 64 + 32), v1);
+                tmem_ld_wait();
+            }
+            const int key0 = j * ATT_BKEY + sub * 64;
+            if (key0 + 64 > p.L) {  // ragged tail: keys beyond L do not take part
+#pragma unroll
+                for (int t = 0; t < 64; ++t)
+                    if (key0 + t >= p.L) v[t] = 0xff800000u;  // -inf
+            }
+            float bm = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+#pragma unroll
+            for (int t = 2; t < 64; t += 2) bm = fmax3(bm, __uint_as_float(v[t]), __uint_as_float(v[t + 1]));
+            float* xb = xchg + (j & 1) * 256;
+            xb[sub * 128 + r] = bm;
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 softmax warps; also: both threads of a row hold their S in registers
+            bm = fmaxf(bm, xb[(sub ^ 1) * 128 + r]);
+            if (j == 0) {
+                mref = bm;
+            } else {
+                const bool need = (bm - mref) * c > AF_TAU;
+                if (__any_sync(0xffffffffu, need)) {
+                    // slow path: move the reference and rescale what has been accumulated under the old one
+                    mbar_wait(smem_u32(&pv_done), (uint32_t)(j - 1) & 1u);
+                    tc_fence_after();
+                    const float f = need ? ex2f((mref - bm) * c) : 1.0f;
+                    uint32_t o[32];
+                    tmem_ld_32x32(t_o + lane_off + (uint32_t)(sub * 32), o);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * f);
+                    tmem_st_32x32(t_o + lane_off + (uint32_t)(sub * 32), o);
+                    lsum2.x *= f, lsum2.y *= f;
+                    if (need) mref = bm;
+                }
+            }
+            const float2 c2 = make_float2(c, c);
+            const float2 nm2 = make_float2(-mref * c, -mref * c);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int t = 0; t < 32; t += 2) {
+                    const float2 x = ffma2(make_float2(__uint_as_float(v[hh * 32 + t]), __uint_as_float(v[hh * 32 + t + 1])), c2, nm2);
+                    const float2 e = make_float2(ex2f(x.x), ex2f(x.y));
+                    lsum2 = fadd2(lsum2, e);
+                    uint32_t h2;
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(e.y), "f"(e.x));
+                    const float2 hf = make_float2(__uint_as_float(h2 << 16), __uint_as_float(h2 & 0xffff0000u));
+                    const float2 d = fsub2(e, hf);
+                    uint32_t l2;
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(d.y), "f"(d.x));
+                    hi[t >> 1] = h2;
+                    lo[t >> 1] = l2;
+                }
+                // keys [64 sub + 32 hh, +32) of the block: 16 columns of the hi half / the lo half of the slot
+                tmem_st_32x16(t_slot + (uint32_t)(sub * 32 + hh * 16), hi);
+                tmem_st_32x16(t_slot + 64u + (uint32_t)(sub * 32 + hh * 16), lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&p_full[slot]));
+        }
+        // ---- epilogue: O / rowsum -> split-bf16 [B*L, H*dh]; thread `sub` stores 32 of the 64 columns ----
+        float lsum = lsum2.x + lsum2.y;
+        float* xb = xchg + (nkb & 1) * 256;
+        xb[sub * 128 + r] = lsum;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        lsum += xb[(sub ^ 1) * 128 + r];
+        mbar_wait(smem_u32(&pv_done), (uint32_t)(nkb - 1) & 1u);
+        tc_fence_after();
+        const int qrow = q_tile * ATT_BQ + r;
+        const float inv = 1.0f / lsum;
+        __nv_bfloat16* ohi = p.out_hi + (long long)b * p.out_b + (long long)h * p.out_h + (long long)qrow * p.ldo;
+        __nv_bfloat16* olo = ohi + p.out_plane;
+        {
+            uint32_t o[32];
+            tmem_ld_32x32(t_o + lane_off + (uint32_t)(sub * 32), o);
+            tmem_ld_wait();
+            if (qrow < p.L) {
+#pragma unroll
+                for (int t = 0; t < 32; t += 8) {
+                    uint32_t hh[4], ll[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        split_bf16(__uint_as_float(o[t + 2 * u]) * inv, h0, l0);
+                        split_bf16(__uint_as_float(o[t + 2 * u + 1]) * inv, h1, l1);
+                        hh[u] = pack_bf16x2(h0, h1);
+                        ll[u] = pack_bf16x2(l0, l1);
+                    }
+                    *reinterpret_cast<uint4*>(ohi + sub * 32 + t) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                    *reinterpret_cast<uint4*>(olo + sub * 32 + t) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 int make_operand_map_ext(CUtensorMap* map, const psam_operand* op, int box_rows, int box_planes);  // gemm_tc.cu
+
+}  // namespace psam
+
+namespace psam {
+
+static int attention_setup(const psam_operand* q, const psam_operand* k, const psam_operand* v, void* out_hi, long long out_plane,
+                           long long ldo, long long out_head_stride, long long out_cloud_stride, float scale, CUtensorMap* mq,
+                           CUtensorMap* mk, CUtensorMap* mv, AttnParams* p, dim3* grid) {
+    if (!q || !k || !v || !out_hi) return PSAM_ERR_ARG;
+    const int L = q->rows, dh = q->k;
+    const int H = q->nb1 > 0 ? q->nb1 : 1, B = q->nb2 > 0 ? q->nb2 : 1;
+    if (dh != ATT_DH || L <= 0) return PSAM_ERR_UNSUPPORTED;
+    if (k->rows != L || v->rows != L || k->k != dh || v->k != dh) return PSAM_ERR_ARG;
+    if ((ldo | out_plane | out_head_stride | out_cloud_stride) & 7) return PSAM_ERR_ARG;
+    int rc = make_operand_map_ext(mq, q, ATT_BQ, 2);
+    if (rc) return rc;
+    rc = make_operand_map_ext(mk, k, ATT_BKEY, 2);
+    if (rc) return rc;
+    rc = make_operand_map_ext(mv, v, ATT_BKEY, 2);
+    if (rc) return rc;
+    p->L = L, p->H = H, p->B = B;
+    p->scale_log2e = scale * 1.4426950408889634f;
+    p->out_hi = (__nv_bfloat16*)out_hi;
+    p->out_plane = out_plane, p->ldo = ldo, p->out_h = out_head_stride, p->out_b = out_cloud_stride;
+    *grid = dim3((unsigned)ceil_div(L, ATT_BQ), (unsigned)H, (unsigned)B);
+    return PSAM_OK;
+}
 
 }  // namespace psam
 
@@ -557,26 +919,27 @@ extern "C" int psam_attention_bf16x3(const psam_operand* q, const psam_operand* 
                                      long long out_plane, long long ldo, long long out_head_stride,
                                      long long out_cloud_stride, float scale, cudaStream_t stream) {
     using namespace psam;
-    if (!q || !k || !v || !out_hi) return PSAM_ERR_ARG;
-    const int L = q->rows, dh = q->k;
-    const int H = q->nb1 > 0 ? q->nb1 : 1, B = q->nb2 > 0 ? q->nb2 : 1;
-    if (dh != ATT_DH || L <= 0) return PSAM_ERR_UNSUPPORTED;
-    if (k->rows != L || v->rows != L || k->k != dh || v->k != dh) return PSAM_ERR_ARG;
-    if ((ldo | out_plane | out_head_stride | out_cloud_stride) & 7) return PSAM_ERR_ARG;
     CUtensorMap mq, mk, mv;
-    int rc = make_operand_map_ext(&mq, q, ATT_BQ, 2);
-    if (rc) return rc;
-    rc = make_operand_map_ext(&mk, k, ATT_BKEY, 2);
-    if (rc) return rc;
-    rc = make_operand_map_ext(&mv, v, ATT_BKEY, 2);
-    if (rc) return rc;
     AttnParams p;
-    p.L = L, p.H = H, p.B = B;
-    p.scale_log2e = scale * 1.4426950408889634f;
-    p.out_hi = (__nv_bfloat16*)out_hi;
-    p.out_plane = out_plane, p.ldo = ldo, p.out_h = out_head_stride, p.out_b = out_cloud_stride;
-    dim3 grid((unsigned)ceil_div(L, ATT_BQ), (unsigned)H, (unsigned)B);
-    if (L > 512) {  // two-sweep kernel: S streamed through a ring of TMEM slots
+    dim3 grid;
+    int rc = attention_setup(q, k, v, out_hi, out_plane, ldo, out_head_stride, out_cloud_stride, scale, &mq, &mk, &mv, &p, &grid);
+    if (rc) return rc;
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_TOTAL));
+    PSAM_CUDA_TRY(psam::launch(attention_flow_kernel, dim3(grid), dim3(ATT_THREADS), (size_t)(AF_SMEM_TOTAL), stream, mq, mk, mv, p));
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_attention_bf16x3_twopass(const psam_operand* q, const psam_operand* k, const psam_operand* v, void* out_hi,
+                                             long long out_plane, long long ldo, long long out_head_stride,
+                                             long long out_cloud_stride, float scale, cudaStream_t stream) {
+    using namespace psam;
+    CUtensorMap mq, mk, mv;
+    AttnParams p;
+    dim3 grid;
+    int rc = attention_setup(q, k, v, out_hi, out_plane, ldo, out_head_stride, out_cloud_stride, scale, &mq, &mk, &mv, &p, &grid);
+    if (rc) return rc;
+    if (p.L > 512) {  // two-sweep kernel: S streamed through a ring of TMEM slots
         PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL));
         attention_tc_long_kernel<<<grid, ATT_THREADS, ATT_SMEM_TOTAL, stream>>>(mq, mk, mv, p);
         PSAM_LAUNCH_CHECK();

@@ -31,8 +31,11 @@ namespace psam {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_EPI_PER_QUARTER = 4;
-constexpr int GEMM_THREADS = 64 + 128 * GEMM_EPI_PER_QUARTER;  // TMA warp, MMA warp, 16 epilogue warps (four per TMEM lane quarter)
+constexpr int GEMM_EPI_PER_QUARTER = 4;                         // default: 16 epilogue warps (four per TMEM lane quarter)
+constexpr int gemm_threads(int epq) { return 64 + 128 * epq; }  // TMA warp, MMA warp, 4*epq epilogue warps
+constexpr int GEMM_THREADS = gemm_threads(GEMM_EPI_PER_QUARTER);
+// psam_gemm_out.variant bits (experiment / policy switches; no environment variable is read inside the library)
+constexpr int GV_2CTA = 0x1, GV_BK32 = 0x2, GV_SCALAR_EPI = 0x4, GV_DUAL = 0x8, GV_NO_DUAL = 0x10;
 
 struct GemmEpilogue {
     float* out_f32;            // may be null
@@ -307,7 +310,8 @@ __device__ __forceinline__ void epi_chunk_v4_dispatch(float* stg, const uint32_t
 // coalesced global accesses (lane = column: every store/load/red touches one contiguous 128-byte row segment).
 __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const GemmEpilogue& ep, unsigned char* smem_aligned,
                                               uint32_t tmem_base, uint32_t tmem_full_bar_addr, int warp, int lane, int m_tile,
-                                              int n_tile, int b1, int b2, int split, int num_kb, int BN) {
+                                              int n_tile, int b1, int b2, int split, int num_kb, int BN,
+                                              int epq = GEMM_EPI_PER_QUARTER) {
         const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
         const int row0 = m_tile * GEMM_BM + quarter * 32;
         if (num_kb > 0) {
@@ -324,7 +328,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const Gemm
         const bool add_bias = ep.bias && split == 0;
         const int nchunks = BN / 32;
 #pragma unroll 1
-        for (int c = ehalf; c < nchunks; c += GEMM_EPI_PER_QUARTER) {
+        for (int c = ehalf; c < nchunks; c += epq) {
             const int col0 = n_tile * BN + c * 32;
             if (col0 >= shape.N) break;
             uint32_t v[32];
@@ -423,8 +427,13 @@ __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const Gemm
 
 // BK = 64: rows of 128 B, SWIZZLE_128B.  BK = 32: rows of 64 B, SWIZZLE_64B - half-size stages, twice as many of them
 // in flight (finer-grained pipeline; the wide-tile throughput configuration otherwise has only 2 stages).
-template <int MAXBN, int STAGES, int BK>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// EPQ = epilogue warps per TMEM lane quarter, RES = CTAs of this kernel that must fit one SM.  <256, 2, 32, 2, 2> is the
+// DUAL-RESIDENT configuration of the throughput policy: 97 KB of shared memory, 256 TMEM columns and 320 threads per CTA,
+// so two CTAs (usually of different clouds' launches) share an SM and one's TMA ramp-up / epilogue overlaps the other's
+// MMAs - with one 197 KB CTA per SM the tensor pipe idles for about half of every CTA's lifetime
+// (profiles/r01_gemm_qkv_bn256_ncu_full.md: 49.6 % active).
+template <int MAXBN, int STAGES, int BK, int EPQ = GEMM_EPI_PER_QUARTER, int RES = 1>
+__global__ void __launch_bounds__(gemm_threads(EPQ), RES)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_bmc, const GemmShape shape, const GemmEpilogue ep) {
     pdl_launch_dependents();
@@ -548,7 +557,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // ===================== epilogue (warps 2..9) =====================
         // TMEM -> registers (thread = row) -> per-warp smem transpose -> coalesced global accesses
         // (lane = column: every store/load/red instruction touches one contiguous 128-byte row segment).
-        gemm_epilogue(shape, ep, smem_aligned, tmem_base, smem_u32(&tmem_full_bar), warp, lane, m_tile, n_tile, b1, b2, split, num_kb, BN);
+        gemm_epilogue(shape, ep, smem_aligned, tmem_base, smem_u32(&tmem_full_bar), warp, lane, m_tile, n_tile, b1, b2, split, num_kb, BN, EPQ);
     }
 
     tc_fence_before();
@@ -757,16 +766,16 @@ int make_operand_map_ext(CUtensorMap* map, const psam_operand* op, int box_rows,
     return make_operand_map(map, op, box_rows, box_planes);
 }
 
-template <int MAXBN, int STAGES, int BK = 64>
+template <int MAXBN, int STAGES, int BK = 64, int EPQ = GEMM_EPI_PER_QUARTER, int RES = 1>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbmc, const GemmShape& sh,
                        const GemmEpilogue& ep, cudaStream_t stream) {
-    auto kern = gemm_tc_kernel<MAXBN, STAGES, BK>;
+    auto kern = gemm_tc_kernel<MAXBN, STAGES, BK, EPQ, RES>;
     using S = GemmSmem<MAXBN, STAGES, BK>;
     PSAM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     const int mt = ceil_div(ceil_div(sh.M, GEMM_BM), sh.cm) * sh.cm;  // pad the m-tiles to whole clusters
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)ceil_div(sh.N, sh.bn), (unsigned)mt, (unsigned)(sh.nb1 * sh.nb2 * sh.split_k));
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(gemm_threads(EPQ));
     cfg.dynamicSmemBytes = S::TOTAL;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
@@ -858,8 +867,8 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     if ((w->nb1 > 0 ? w->nb1 : 1) != sh.nb1 || (w->nb2 > 0 ? w->nb2 : 1) != sh.nb2) return PSAM_ERR_ARG;
     sh.split_k = split_k;
     sh.passes = passes;
-    sh.prefetch = 0;
-    if (const char* e = getenv("PSAM_GEMM_PREFETCH")) sh.prefetch = atoi(e);
+    const int variant = o->variant;
+    sh.prefetch = (variant >> 12) & 15;  // k-blocks of W to prefetch into L2 ahead of the TMA loads
     GemmEpilogue ep;
     ep.out_f32 = o->out_f32, ep.ldo = o->ldo, ep.out_b1 = o->out_b1, ep.out_b2 = o->out_b2;
     ep.out_hi = (__nv_bfloat16*)o->out_hi, ep.out_plane = o->out_plane, ep.ldo_s = o->ldo_s;
@@ -871,7 +880,7 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     {
         auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
         auto a8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; };
-        static const bool off = getenv("PSAM_GEMM_SCALAR_EPILOGUE") != nullptr;
+        const bool off = (variant & GV_SCALAR_EPI) != 0;
         bool ok = !off && !ep.rd_out && (!ep.bias || a16(ep.bias));
         if (ep.out_f32) ok = ok && a16(ep.out_f32) && ((ep.ldo | ep.out_b1 | ep.out_b2) & 3) == 0;
         if (ep.resid) ok = ok && a16(ep.resid);
@@ -896,16 +905,11 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     if (ep.swiglu && ((!ep.out_hi == !ep.out_f32) || ep.accumulate || ep.resid || ep.act || (sh.N & 1))) return PSAM_ERR_ARG;
     int bn = choose_bn(sh.M, sh.N, sh.K, sh.nb1 * sh.nb2, sh.split_k, o->tile_hint == 1);
     if (o->tile_hint >= 32 && o->tile_hint <= 256 && o->tile_hint % 32 == 0) bn = o->tile_hint;
-    if (const char* e = getenv("PSAM_GEMM_BN")) {  // tuning override (tools/gemm_bench.py)
-        const int v = atoi(e);
-        if (v >= 32 && v <= 256 && v % 32 == 0) bn = v;
-    }
     sh.bn = bn;
     const int mtiles = ceil_div(sh.M, GEMM_BM);
-    // 2-CTA path (cta_group::2): pairs of m-tiles, each CTA streams half of the W tile.  PSAM_GEMM_2CTA=1|0 forces it.
+    // 2-CTA path (cta_group::2): pairs of m-tiles, each CTA streams half of the W tile.  Opt-in: variant bit 0x1.
     {
-        int use2 = 0;
-        if (const char* e = getenv("PSAM_GEMM_2CTA")) use2 = atoi(e);
+        const int use2 = variant & GV_2CTA;
         if (use2 && mtiles >= 2 && sh.N >= 128) {
             int bn2 = (o->tile_hint == 1 || sh.N >= 256) ? 256 : 128;
             if (o->tile_hint >= 64 && o->tile_hint <= 256 && o->tile_hint % 64 == 0) bn2 = o->tile_hint;
@@ -923,10 +927,10 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     // CTAs of consecutive m-tiles form a cluster and share each W tile through TMA multicast
     // MEASURED (B200, config c2, 8 clouds in flight): cluster 4 -> 581 clouds/s, no cluster -> 626 clouds/s: the L2
     // already merges the concurrent requests of the 4 m-tile CTAs for the same W lines, and the cluster couples their
-    // progress.  Multicast therefore stays opt-in (PSAM_GEMM_CLUSTER=2|4).
+    // progress.  Multicast therefore stays opt-in (variant bits 8-11 = cluster size 2|4).
     int cm = 1;
-    if (const char* e = getenv("PSAM_GEMM_CLUSTER")) {
-        const int v = atoi(e);
+    {
+        const int v = (variant >> 8) & 15;
         const int cap = mtiles >= 4 ? 4 : (mtiles >= 2 ? 2 : 1);
         if (v == 1 || v == 2 || v == 4) cm = v < cap ? v : cap;
     }
@@ -939,18 +943,16 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     if (rc) return rc;
     rc = make_operand_map(&mbmc, w, bn / cm, 1);
     if (rc) return rc;
-    // wide tiles: BK = 32 (64-byte swizzle) gives 4 half-size stages instead of 2.  MEASURED: 611 vs 618 clouds/s
-    // (config c2, 8 clouds in flight) - no gain, so it is opt-in (PSAM_GEMM_BK32=1).
-    static int bk32 = -1;
-    if (bk32 < 0) {
-        const char* e = getenv("PSAM_GEMM_BK32");
-        bk32 = (e && e[0] == '1') ? 1 : 0;
-    }
-    if (bn > 160 && cm == 1 && bk32) {
+    // wide tiles, throughput policy: the dual-resident configuration (two 97 KB CTAs per SM, BK = 32, 2 stages each);
+    // GV_DUAL forces it for any wide tile, GV_NO_DUAL keeps the one-CTA-per-SM kernel.
+    // GV_BK32: one CTA per SM with 4 half-size stages.  MEASURED round 1: 611 vs 618 clouds/s - no gain, opt-in.
+    const bool dual = bn > 160 && cm == 1 && ((variant & GV_DUAL) || (o->tile_hint == 1 && !(variant & GV_NO_DUAL)));
+    if (bn > 160 && cm == 1 && (dual || (variant & GV_BK32))) {
         rc = make_operand_map(&ma, a, GEMM_BM, passes == 3 ? 2 : 1, 32);
         if (rc) return rc;
         rc = make_operand_map(&mb, w, bn, passes == 3 ? 2 : 1, 32);
         if (rc) return rc;
+        if (dual) return launch_gemm<256, 2, 32, 2, 2>(ma, mb, mb, sh, ep, stream);
         return launch_gemm<256, 4, 32>(ma, mb, mb, sh, ep, stream);
     }
     if (bn <= 64) return launch_gemm<64, 4>(ma, mb, mbmc, sh, ep, stream);

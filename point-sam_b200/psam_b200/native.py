@@ -31,7 +31,8 @@ class GemmOut(Structure):
                 ("bias", c_void_p), ("resid", c_void_p), ("alpha", c_float), ("act", c_int), ("accumulate", c_int),
                 ("swiglu", c_int), ("tile_hint", c_int), ("gmax", c_void_p), ("ld_gmax", c_longlong), ("group_rows", c_int),
                 ("rd_w", c_void_p), ("rd_out", c_void_p), ("rd_rows", c_int), ("rd_c", c_int),
-                ("stats_out", c_void_p), ("ln_stats", c_void_p), ("ln_c", c_void_p), ("ln_h", c_int), ("ln_eps", c_float)]
+                ("stats_out", c_void_p), ("ln_stats", c_void_p), ("ln_c", c_void_p), ("ln_h", c_int), ("ln_eps", c_float),
+                ("variant", c_int)]
 
 
 class LinearArgs(Structure):
@@ -56,7 +57,7 @@ class LnArgs(Structure):
 EXPORTS = [
     "psam_fps_workspace_bytes", "psam_fps_f32", "psam_knn_f32", "psam_group_gather_f32", "psam_knn3_interp_f32", "psam_nn_distance_f32",
     "psam_border_prompt_workspace_bytes", "psam_border_prompt_f32",
-    "psam_gemm_bf16x3", "psam_attention_bf16x3", "psam_linear_f32", "psam_layernorm_f32", "psam_swiglu_ln", "psam_small_in_linear",
+    "psam_gemm_bf16x3", "psam_attention_bf16x3", "psam_attention_bf16x3_twopass", "psam_linear_f32", "psam_layernorm_f32", "psam_swiglu_ln", "psam_small_in_linear",
     "psam_group_max", "psam_softmax_split", "psam_transpose_split", "psam_posenc_f32", "psam_attention_f32",
     "psam_decoder_prepare", "psam_interp_ln_gelu", "psam_mask_dot", "psam_add_bcast_f32", "psam_split_f32",
     "psam_version",
@@ -86,6 +87,7 @@ def lib():
             "psam_border_prompt_f32": [p, p, p, p, i, i, i, i, p, p, p, p, p],
             "psam_gemm_bf16x3": [POINTER(Operand), POINTER(Operand), POINTER(GemmOut), i, i, p],
             "psam_attention_bf16x3": [POINTER(Operand), POINTER(Operand), POINTER(Operand), p, ll, ll, ll, ll, f, p],
+            "psam_attention_bf16x3_twopass": [POINTER(Operand), POINTER(Operand), POINTER(Operand), p, ll, ll, ll, ll, f, p],
             "psam_linear_f32": [POINTER(LinearArgs), p],
             "psam_layernorm_f32": [POINTER(LnArgs), p],
             "psam_swiglu_ln": [p, ll, ll, i, i, p, p, f, p, ll, ll, ll, p],

@@ -123,11 +123,17 @@ def border_prompt(coords: torch.Tensor, gt_masks: torch.Tensor, pred_logits: Opt
 
 
 GEMM_TILE_HINT = 0  # 0 = latency-optimal tiles, 1 = SM-time-optimal tiles (set by PipelinedPredictor)
+GEMM_TILE_BN = 0    # 32..256: explicit tile width (experiments / tests)
+# psam_gemm_out.variant (experiment switches, see include/psam_b200.h); PSAM_GEMM_VARIANT seeds it once at import
+GV_2CTA, GV_BK32, GV_SCALAR_EPI, GV_DUAL, GV_NO_DUAL = 0x1, 0x2, 0x4, 0x8, 0x10
+GEMM_VARIANT = int(__import__("os").environ.get("PSAM_GEMM_VARIANT", "0"), 0)
 
 
 def gemm_raw(a: Operand, w: Operand, out: GemmOut, passes: int = 3, split_k: int = 1):
     if out.tile_hint == 0:
-        out.tile_hint = GEMM_TILE_HINT
+        out.tile_hint = GEMM_TILE_BN if GEMM_TILE_BN else GEMM_TILE_HINT
+    if out.variant == 0:
+        out.variant = GEMM_VARIANT
     nv.check(nv.lib().psam_gemm_bf16x3(byref(a), byref(w), byref(out), passes, split_k, nv.stream()), "gemm_bf16x3")
 
 

@@ -445,10 +445,7 @@ def test_linear_attention_posenc_misc():
     torch.testing.assert_close(got.reshape(4, 48), want, atol=0, rtol=0)
 
 
-@pytest.mark.parametrize("B,H,L", [(1, 16, 512), (2, 3, 128), (2, 2, 200), (1, 4, 333), (1, 2, 64),
-                                   (1, 2, 640), (2, 3, 1000), (1, 16, 2048), (1, 1, 513), (1, 2, 3000)])
-def test_fused_attention_tc(B, H, L):
-    """psam_attention_bf16x3 (S in TMEM, exact softmax, MN-major V; two-sweep ring kernel for L > 512) vs fp64 attention."""
+def _attention_case(qkv, B, H, L, entry):
     from ctypes import byref
 
     from psam_b200 import native as nv
@@ -456,39 +453,63 @@ def test_fused_attention_tc(B, H, L):
     ops = _ops()
     dh = 64
     D = H * dh
-    qkv = _rand(B * L, 3 * D, seed=21)
     QKV = ops.Split(B * L, 3 * D, _dev())
     ops.split_f32(qkv, QKV)
     att = ops.Split(B * L, D, _dev())
+    att.t.fill_(float("nan"))
     mk = lambda col: QKV.operand(rows=L, k=dh, col=col, nb1=H, b1_stride=dh, nb2=B, b2_stride=L * QKV.pitch)
     qa, ka, va = mk(0), mk(D), mk(2 * D)
-    nv.check(nv.lib().psam_attention_bf16x3(byref(qa), byref(ka), byref(va), att.ptr(), att.plane, att.pitch, dh,
-                                           L * att.pitch, dh ** -0.5, nv.stream()), "attention_bf16x3")
+    nv.check(getattr(nv.lib(), entry)(byref(qa), byref(ka), byref(va), att.ptr(), att.plane, att.pitch, dh,
+                                      L * att.pitch, dh ** -0.5, nv.stream()), entry)
     x = qkv.double().reshape(B, L, 3, H, dh).permute(2, 0, 3, 1, 4)
     want = (torch.softmax(x[0] @ x[1].transpose(-1, -2) * dh ** -0.5, -1) @ x[2]).transpose(1, 2).reshape(B * L, D).float()
-    err = float((att.float() - want).abs().max())
+    return att.float(), want
+
+
+@pytest.mark.parametrize("entry", ["psam_attention_bf16x3", "psam_attention_bf16x3_twopass"])
+@pytest.mark.parametrize("B,H,L", [(1, 16, 512), (2, 3, 128), (2, 2, 200), (1, 4, 333), (1, 2, 64), (1, 3, 7),
+                                   (1, 2, 640), (2, 3, 1000), (1, 16, 2048), (1, 1, 513), (1, 2, 3000)])
+def test_fused_attention_tc(B, H, L, entry):
+    """psam_attention_bf16x3 (streaming kernel: S ring in TMEM, P written back into TMEM as the A operand of the PV MMA,
+    lazily moved reference maximum) and the first-generation two-pass kernels vs fp64 attention."""
+    got, want = _attention_case(_rand(B * L, 3 * 64 * H, seed=21), B, H, L, entry)
+    err = float((got - want).abs().max())
     assert err < 5e-5 * max(1.0, float(want.abs().max())), err
 
 
-@pytest.mark.parametrize("variant", ["bn256_bk32", "bn256_bk64", "two_cta", "cluster4"])
-def test_gemm_tc_variants(variant, monkeypatch):
-    """Opt-in / policy-selected GEMM variants: wide tiles with 64-byte-swizzled half-depth stages (throughput policy),
-    the same with 128-byte swizzle, the 2-CTA cta_group::2 kernel, and W-tile multicast over a 4-CTA cluster."""
-    ops = _ops()
-    env = {"bn256_bk32": {"PSAM_GEMM_BN": "256", "PSAM_GEMM_BK32": "1"}, "bn256_bk64": {"PSAM_GEMM_BN": "256", "PSAM_GEMM_BK32": "0"},
-           "two_cta": {"PSAM_GEMM_2CTA": "1"}, "cluster4": {"PSAM_GEMM_CLUSTER": "4", "PSAM_GEMM_BN": "128"}}[variant]
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    if variant == "bn256_bk32" and os.environ.get("PSAM_GEMM_BK32_LATCHED", "") != "1":
-        # the switch is read once per process; run this variant in a fresh interpreter
-        import subprocess
-        import sys
+@pytest.mark.parametrize("L", [512, 1100])
+def test_fused_attention_tc_reference_maximum_moves(L):
+    """Logits that grow from key block to key block (by far more than the 2^8 slack) force the rare slow path of the
+    streaming kernel: the reference maximum moves and O is rescaled in tensor memory - several times per row, for a
+    subset of rows only (rows whose query is negated see DEcreasing logits and never rescale)."""
+    B, H, dh = 1, 2, 64
+    D = H * dh
+    g = torch.Generator(device="cpu").manual_seed(5)
+    qkv = torch.randn(B * L, 3 * D, generator=g)
+    ramp = (torch.arange(L) // 128).float()[:, None]            # key block index
+    qkv[:, :D] = torch.randn(L, D, generator=g) * 0.2 + 1.0     # queries: common positive direction ...
+    qkv[::3, :D] *= -1.0                                         # ... every third row negated
+    qkv[:, D:2 * D] = torch.randn(L, D, generator=g) * 0.2 + 2.0 * ramp  # keys grow with the block index
+    qkv = qkv.to(_dev())
+    got, want = _attention_case(qkv, B, H, L, "psam_attention_bf16x3")
+    err = float((got - want).abs().max())
+    assert err < 5e-5 * max(1.0, float(want.abs().max())), err
+    got2, _ = _attention_case(qkv, B, H, L, "psam_attention_bf16x3_twopass")
+    assert float((got - got2).abs().max()) < 5e-5 * max(1.0, float(want.abs().max()))
 
-        code = ("import os, sys; os.environ['PSAM_GEMM_BK32_LATCHED'] = '1'; import pytest; "
-                "sys.exit(pytest.main(['-q', '-m', 'gpu', '-p', 'no:cacheprovider', %r + '::test_gemm_tc_variants', '-k', 'bn256_bk32']))" % __file__)
-        env = dict(os.environ, PSAM_GEMM_BK32="1", PSAM_GEMM_BN="256")
-        assert subprocess.call([sys.executable, "-c", code], env=env) == 0
-        return
+
+@pytest.mark.parametrize("variant", ["bn256_bk32", "bn256_bk64", "two_cta", "cluster4", "dual_resident", "throughput_policy"])
+def test_gemm_tc_variants(variant, monkeypatch):
+    """Opt-in / policy-selected GEMM variants (psam_gemm_out.variant / tile_hint; the library reads no environment):
+    wide tiles with 64-byte-swizzled half-depth stages, the same with 128-byte swizzle, the 2-CTA cta_group::2 kernel,
+    W-tile multicast over a 4-CTA cluster, the dual-resident wide-tile kernel (two CTAs per SM) forced, and whatever the
+    throughput policy (tile_hint = 1, as baked into the pipelined predictor's graphs) selects."""
+    ops = _ops()
+    bn, var, hint = {"bn256_bk32": (256, ops.GV_BK32, 0), "bn256_bk64": (256, ops.GV_NO_DUAL, 0), "two_cta": (0, ops.GV_2CTA, 0),
+                     "cluster4": (128, 4 << 8, 0), "dual_resident": (256, ops.GV_DUAL, 0), "throughput_policy": (0, 0, 1)}[variant]
+    monkeypatch.setattr(ops, "GEMM_TILE_BN", bn)
+    monkeypatch.setattr(ops, "GEMM_VARIANT", var)
+    monkeypatch.setattr(ops, "GEMM_TILE_HINT", hint)
     for (M, N, K, sk) in [(512, 3072, 1024, 1), (512, 1024, 2752, 4), (640, 520, 200, 1), (32768, 512, 128, 1)]:
         a, w, b = _rand(M, K, seed=31), _rand(N, K, seed=32, scale=K ** -0.5), _rand(N, seed=33)
         A, W = ops.pack_weight(a), ops.pack_weight(w)
