@@ -115,13 +115,16 @@ typedef struct {
     const float* rd_w;      /* optional fused row-dot (replaces masks = hyper_in @ upscaled^T, mask_decoder.py:176):        */
     float* rd_out;          /*   rd_out[z, c, n] += sum_col act(alpha*acc + bias)[z*rd_rows + n, col] * rd_w[z, c, col]    */
     int rd_rows, rd_c;      /*   rd_out pre-zeroed [Z, rd_c, rd_rows]; rd_rows % 32 == 0; rd_c <= 8; no other output allowed */
-    float* stats_out;       /* with swiglu + out_hi: the products go out as split-bf16 and stats_out[row] (2 floats, pre-zeroed)
-                             * accumulates (sum, sum of squares) of the row - the statistics of timm's SwiGLU.norm */
-    const float* ln_stats;  /* LayerNorm folded into this GEMM (the LN that follows SwiGLU feeds fc2 directly): A = the
-                             * un-normalised rows, W pre-multiplied by gamma, ln_c[n] = sum_k gamma_k W[n,k], bias[n] =
-                             * sum_k beta_k W[n,k] + b[n];  out = rstd_row * (acc - mean_row * ln_c[n]) + bias[n] with
-                             * mean / rstd from ln_stats[row] = (sum, sum sq) over ln_h columns.  Works with accumulate /
-                             * split_k (each split scales its partial sum) and with resid. */
+    float* stats_out;       /* stats_out[row] (2 floats, pre-zeroed) accumulates (sum, sum of squares) of the row this GEMM
+                             * WRITES as split-bf16 - the statistics a LayerNorm-folded consumer GEMM needs: with swiglu +
+                             * out_hi the SwiGLU products (timm SwiGLU.norm), otherwise (out_hi, split_k == 1, no
+                             * accumulate) the final values after bias / residual / activation (norm1 / norm2 / fc_norm) */
+    const float* ln_stats;  /* LayerNorm folded into this GEMM: A = the un-normalised rows, W pre-multiplied by gamma,
+                             * ln_c[n] = sum_k gamma_k W[n,k], bias[n] = sum_k beta_k W[n,k] + b[n];
+                             * out = act(rstd_row * (acc - mean_row * ln_c[n]) + bias[n] (+ resid)) with mean / rstd from
+                             * ln_stats[row] = (sum, sum sq) over ln_h columns.  Works with every output form of the
+                             * vectorised epilogue (fp32, split-bf16, SwiGLU pairs) and with accumulate / split_k (each
+                             * split scales its partial sum). */
     const float* ln_c;
     int ln_h;
     float ln_eps;

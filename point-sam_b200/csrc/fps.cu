@@ -7,11 +7,12 @@
 // Design: one thread-block CLUSTER per cloud.  The cloud (xyz + running min-distance) lives in the
 // registers of the cluster's threads for the whole kernel, so an iteration touches no global memory.
 // Per iteration every warp reduces its candidates with redux.sync into one 20-byte record (max-distance
-// bits, tie-break priority, xyz of the candidate); the CTA combines its warps' records through shared
-// memory (one __syncthreads) and warp 0 pushes the CTA record into the shared memory of EVERY CTA of the
-// cluster with st.async (DSMEM store that completes transaction bytes on the receiver's mbarrier - data
-// and signal in a single hop).  All threads then wait on their local mbarrier and reduce the C records.
-// No barrier.cluster inside the loop.
+// bits, tie-break priority, xyz of the candidate) and pushes it straight into the shared memory of EVERY
+// CTA of the cluster with st.async (DSMEM store that completes transaction bytes on the receiver's
+// mbarrier - data and signal in a single hop).  All threads then wait on their local mbarrier and reduce
+// the C x 8 records.  No __syncthreads, no barrier.cluster and no second reduction stage inside the loop
+// (round 1 combined the warps of a CTA through shared memory first: one block barrier plus a serial
+// warp-0 stage per iteration, 0.77 us/iteration at N = 32768).
 //
 // Bit-exactness: squared distance is fmaf(dz,dz,fmaf(dy,dy,dx*dx)) with d = p_j - p_sel, and among
 // equal maxima the winner is the lexicographic minimum of (bitrev(j mod T), j div T), T = the
@@ -44,10 +45,8 @@ __global__ void __launch_bounds__(FPS_THREADS, 1)
 fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long long* __restrict__ idx_out,
                    float* __restrict__ centers_out, float* __restrict__ ws) {
     pdl_prologue();
-    __shared__ __align__(16) uint4 slot_a[2][FPS_MAX_CLUSTER];  // records received from the cluster {bits, prio, x, y}
-    __shared__ float slot_z[2][FPS_MAX_CLUSTER];
-    __shared__ __align__(16) uint4 wrec_a[2][FPS_WARPS];        // per-warp records of this CTA
-    __shared__ float wrec_z[2][FPS_WARPS];
+    __shared__ __align__(16) uint4 slot_a[2][FPS_MAX_SLOTS];  // records received from every warp of the cluster {bits, prio, x, y}
+    __shared__ float slot_z[2][FPS_MAX_SLOTS];
     __shared__ __align__(8) uint64_t mbar[2];
 
     const uint32_t C = cluster_nctarank();
@@ -58,7 +57,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long 
     const uint32_t qmask = (1u << (32 - log2T)) - 1u;
     const int stride = (int)C * FPS_THREADS;
     const int gt = (int)rank * FPS_THREADS + tid;
-    const uint32_t tx_bytes = C * 20u;  // every peer (incl. this CTA) delivers 16 + 4 bytes per iteration
+    const uint32_t tx_bytes = C * FPS_WARPS * 20u;  // every warp of every peer (incl. this CTA) delivers 16 + 4 bytes per iteration
 
     xyz += (size_t)cloud * N * 3;
     idx_out += (size_t)cloud * G;
@@ -146,36 +145,25 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long 
             if (bestbits != wmax) myprio = 0xFFFFFFFFu;
         }
         const uint32_t wprio = __reduce_min_sync(0xffffffffu, myprio);
-        if (myprio == wprio && bestbits == wmax) {  // exactly one lane (priorities are unique per point)
-            wrec_a[p][warp] = make_uint4(wmax, wprio, __float_as_uint(wx), __float_as_uint(wy));
-            wrec_z[p][warp] = wz;
-        }
-        __syncthreads();
-        // ---- 3. warp 0: CTA record -> every CTA of the cluster (st.async, lane c serves peer c) --
-        if (warp == 0) {
-            uint4 a = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);
-            float z = 0.f;
-            if (lane < FPS_WARPS) {
-                a = wrec_a[p][lane];
-                z = wrec_z[p][lane];
-            }
-            const uint32_t cmax = __reduce_max_sync(0xffffffffu, a.x);
-            const uint32_t cprio = __reduce_min_sync(0xffffffffu, a.x == cmax ? a.y : 0xFFFFFFFFu);
-            const int src = __ffs(__ballot_sync(0xffffffffu, a.x == cmax && a.y == cprio)) - 1;
-            const uint32_t ox = __shfl_sync(0xffffffffu, a.z, src);
-            const uint32_t oy = __shfl_sync(0xffffffffu, a.w, src);
-            const uint32_t oz = __shfl_sync(0xffffffffu, __float_as_uint(z), src);
+        // ---- 3. every warp pushes ITS record straight into every CTA of the cluster (lane c serves peer c): no
+        //         shared-memory staging, no __syncthreads, no second reduction stage on the critical path ----------
+        {
+            const int src = __ffs(__ballot_sync(0xffffffffu, myprio == wprio && bestbits == wmax)) - 1;  // exactly one lane
+            const uint32_t ox = __shfl_sync(0xffffffffu, __float_as_uint(wx), src);
+            const uint32_t oy = __shfl_sync(0xffffffffu, __float_as_uint(wy), src);
+            const uint32_t oz = __shfl_sync(0xffffffffu, __float_as_uint(wz), src);
             if ((uint32_t)lane < C) {
-                const uint32_t ra = mapa_shared(smem_u32(&slot_a[p][rank]), lane);
-                const uint32_t rz = mapa_shared(smem_u32(&slot_z[p][rank]), lane);
+                const int slot = (int)rank * FPS_WARPS + warp;
+                const uint32_t ra = mapa_shared(smem_u32(&slot_a[p][slot]), lane);
+                const uint32_t rz = mapa_shared(smem_u32(&slot_z[p][slot]), lane);
                 const uint32_t rb = mapa_shared(smem_u32(&mbar[p]), lane);
                 asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-                             ::"r"(ra), "r"(cmax), "r"(cprio), "r"(ox), "r"(oy), "r"(rb) : "memory");
+                             ::"r"(ra), "r"(wmax), "r"(wprio), "r"(ox), "r"(oy), "r"(rb) : "memory");
                 asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
                              ::"r"(rz), "r"(oz), "r"(rb) : "memory");
             }
         }
-        // ---- 4. wait for the C records of this iteration, re-arm the barrier for iteration it+2 ----
+        // ---- 4. wait for the C x 8 records of this iteration, re-arm the barrier for iteration it+2 ----
         {
             const uint32_t bar = smem_u32(&mbar[p]);
             const uint32_t parity = ((uint32_t)(it - 1) >> 1) & 1u;
@@ -183,12 +171,15 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long 
             }
             if (tid == 0) mbar_arrive_expect_tx(bar, tx_bytes);
         }
-        // ---- 5. reduce the records (every warp redundantly) -----------------------------------
+        // ---- 5. reduce the records (every warp redundantly; lane l folds records l, l+32, ...) ------
         uint4 a = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);
         float z = 0.f;
-        if ((uint32_t)lane < C) {
-            a = slot_a[p][lane];
-            z = slot_z[p][lane];
+        for (int r = lane; r < (int)C * FPS_WARPS; r += 32) {
+            const uint4 b4 = slot_a[p][r];
+            if (b4.x > a.x || (b4.x == a.x && b4.y < a.y)) {
+                a = b4;
+                z = slot_z[p][r];
+            }
         }
         const uint32_t fmax = __reduce_max_sync(0xffffffffu, a.x);
         const uint32_t fprio = __reduce_min_sync(0xffffffffu, a.x == fmax ? a.y : 0xFFFFFFFFu);

@@ -211,12 +211,23 @@ __device__ __forceinline__ void epi_chunk_v4(float* __restrict__ stg, const uint
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + rsub, row = row0 + rr;
+        const bool ok = row < M;
         float4 x = ld4(stg + rr * EPI_PITCH + cg * 4);
+        // pre-activation: plain alpha*acc + bias, or the LayerNorm folded into this GEMM (A = un-normalised rows, W scaled by
+        // gamma): rstd * (acc - mean * c[n]) + bias'[n] with the row statistics accumulated by the producer of A
+        if (ep.ln_stats) {
+            const float2 st = ok ? *reinterpret_cast<const float2*>(ep.ln_stats + 2 * (long long)row) : make_float2(0.f, 1.f);
+            const float mean = st.x * ep.ln_inv_h;
+            const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, st.y * ep.ln_inv_h), 0.f) + ep.ln_eps);
+            const float ra = rstd * alpha, mr = add_bias ? -mean * rstd : 0.f;
+            x.x = fmaf(x.x, ra, fmaf(mr, c4.x, b4.x)), x.y = fmaf(x.y, ra, fmaf(mr, c4.y, b4.y));
+            x.z = fmaf(x.z, ra, fmaf(mr, c4.z, b4.z)), x.w = fmaf(x.w, ra, fmaf(mr, c4.w, b4.w));
+        } else {
+            x.x = fmaf(x.x, alpha, b4.x), x.y = fmaf(x.y, alpha, b4.y), x.z = fmaf(x.z, alpha, b4.z), x.w = fmaf(x.w, alpha, b4.w);
+        }
         if (MODE == EPI_SWIGLU_SPLIT) {
             // product of the (gate, value) pairs -> split-bf16 planes + per-row (sum, sum of squares) for the LayerNorm that
             // the consuming GEMM applies algebraically (the reference normalises silu(g)*x before fc2, timm SwiGLU.norm)
-            x.x = fmaf(x.x, alpha, b4.x), x.y = fmaf(x.y, alpha, b4.y), x.z = fmaf(x.z, alpha, b4.z), x.w = fmaf(x.w, alpha, b4.w);
-            const bool ok = row < M;
             const float p0 = ok ? __fdividef(x.x, 1.0f + __expf(-x.x)) * x.y : 0.f;
             const float p1 = ok ? __fdividef(x.z, 1.0f + __expf(-x.z)) * x.w : 0.f;
             float s1 = p0 + p1, s2 = fmaf(p0, p0, p1 * p1);
@@ -239,19 +250,9 @@ __device__ __forceinline__ void epi_chunk_v4(float* __restrict__ stg, const uint
             }
             continue;
         }
-        if (ep.ln_stats) {
-            const float2 st = row < M ? *reinterpret_cast<const float2*>(ep.ln_stats + 2 * (long long)row) : make_float2(0.f, 1.f);
-            const float mean = st.x * ep.ln_inv_h;
-            const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, st.y * ep.ln_inv_h), 0.f) + ep.ln_eps);
-            const float ra = rstd * alpha, mr = add_bias ? -mean * rstd : 0.f;
-            x.x = fmaf(x.x, ra, fmaf(mr, c4.x, b4.x)), x.y = fmaf(x.y, ra, fmaf(mr, c4.y, b4.y));
-            x.z = fmaf(x.z, ra, fmaf(mr, c4.z, b4.z)), x.w = fmaf(x.w, ra, fmaf(mr, c4.w, b4.w));
-        } else {
-            x.x = fmaf(x.x, alpha, b4.x), x.y = fmaf(x.y, alpha, b4.y), x.z = fmaf(x.z, alpha, b4.z), x.w = fmaf(x.w, alpha, b4.w);
-        }
-        if (row < M) {
-            if (ep.gmax) mx.x = fmaxf(mx.x, x.x), mx.y = fmaxf(mx.y, x.y), mx.z = fmaxf(mx.z, x.z), mx.w = fmaxf(mx.w, x.w);
-            if (MODE == EPI_NONE) continue;
+        if (ok && ep.gmax) mx.x = fmaxf(mx.x, x.x), mx.y = fmaxf(mx.y, x.y), mx.z = fmaxf(mx.z, x.z), mx.w = fmaxf(mx.w, x.w);
+        if (MODE == EPI_NONE) continue;
+        if (ok) {
             if (RES) {
                 const float4 r4 = ld4(res + (long long)row * ep.ldo + col);
                 x.x += r4.x, x.y += r4.y, x.z += r4.z, x.w += r4.w;
@@ -271,6 +272,20 @@ __device__ __forceinline__ void epi_chunk_v4(float* __restrict__ stg, const uint
                 const long long o = (long long)row * ep.ldo_s + col;
                 *reinterpret_cast<uint2*>(ohi + o) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
                 *reinterpret_cast<uint2*>(olo + o) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+            }
+        }
+        if ((MODE == EPI_SPLIT || MODE == EPI_SPLIT_F32) && ep.stats_out) {
+            // the rows this GEMM writes are the A operand of a LayerNorm-folded GEMM: accumulate their (sum, sum of squares)
+            float s1 = ok ? (x.x + x.y) + (x.z + x.w) : 0.f;
+            float s2 = ok ? fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, x.w * x.w))) : 0.f;
+#pragma unroll
+            for (int o = 1; o <= 4; o <<= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (ok && cg == 0) {
+                atomicAdd(ep.stats_out + 2 * (long long)row, s1);
+                atomicAdd(ep.stats_out + 2 * (long long)row + 1, s2);
             }
         }
     }
@@ -891,13 +906,15 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     ep.stats_out = o->stats_out, ep.ln_stats = o->ln_stats, ep.ln_c = o->ln_c;
     ep.ln_inv_h = o->ln_h > 0 ? 1.0f / (float)o->ln_h : 0.f, ep.ln_eps = o->ln_eps;
     // the fused forms exist only in the vectorised epilogue: whole 32-column chunks, aligned rows
-    if ((ep.swiglu && ep.out_hi) || ep.ln_stats) {
+    if ((ep.swiglu && ep.out_hi) || ep.ln_stats || ep.stats_out) {
         if (!ep.vec4 || sh.N % 32 != 0 || sh.nb1 * sh.nb2 != 1) return PSAM_ERR_UNSUPPORTED;
-        if (ep.ln_stats && (!ep.ln_c || o->ln_h <= 0 || ep.swiglu || ep.gmax || ep.act || ep.out_hi ||
+        if (ep.ln_stats && (!ep.ln_c || o->ln_h <= 0 || ep.gmax || ep.rd_out || (ep.swiglu && !ep.out_hi) ||
                             (reinterpret_cast<uintptr_t>(ep.ln_c) & 15) || (reinterpret_cast<uintptr_t>(ep.ln_stats) & 7)))
             return PSAM_ERR_ARG;
-    } else if (ep.stats_out) {
-        return PSAM_ERR_ARG;
+        // row statistics of the OUTPUT: either of the SwiGLU products, or of the rows written as split-bf16 (one writer per
+        // element: no split-K, no accumulate)
+        if (ep.stats_out && !(ep.out_hi && (ep.swiglu || (split_k == 1 && !ep.accumulate)))) return PSAM_ERR_ARG;
+        if (ep.stats_out && (reinterpret_cast<uintptr_t>(ep.stats_out) & 7)) return PSAM_ERR_ARG;
     }
     if (ep.rd_out && (!ep.rd_w || ep.rd_rows <= 0 || ep.rd_rows % 32 || ep.rd_c <= 0 || ep.rd_c > 8 || ep.accumulate || ep.resid || ep.swiglu ||
                       ep.gmax || ep.out_f32 || ep.out_hi || split_k != 1 || sh.nb1 * sh.nb2 != 1)) return PSAM_ERR_ARG;

@@ -24,6 +24,9 @@ FUSED_ATTENTION = True
 FUSED_ATTENTION_LONG = os.environ.get("PSAM_FUSED_ATTENTION_LONG", "1") != "0"
 FUSED_INNER_LN = os.environ.get("PSAM_FUSED_INNER_LN", "1") != "0"  # SwiGLU.norm folded into the fc1 / fc2 GEMM epilogues
 FUSED_MASK_DOT = os.environ.get("PSAM_FUSED_MASK_DOT", "1") != "0"
+# norm1 / norm2 / fc_norm folded into the qkv / fc1 / out_proj GEMMs: the producer of the residual stream (pos_embed, proj and
+# fc2 GEMM epilogues) writes x as fp32 + split-bf16 and accumulates the row statistics, so no LayerNorm kernel runs in a block
+FUSED_BLOCK_LN = os.environ.get("PSAM_FUSED_BLOCK_LN", "1") != "0"
 PASSES = 3  # split-bf16 (fp32-parity) mode; 1 = plain bf16 (fails the 1e-3 parity bound)
 
 
@@ -257,6 +260,14 @@ def validate_transformer(tr) -> list:
     return tail
 
 
+def _fold_ln(w: torch.Tensor, b: torch.Tensor, norm):
+    """(W * gamma packed split-bf16, c = (W * gamma) 1, b' = W beta + b) in fp64 -> fp32."""
+    wd = w.detach().double()
+    g, be = norm.weight.detach().double(), norm.bias.detach().double()
+    wg = wd * g[None, :]
+    return ops.pack_weight(wg.float()), wg.sum(dim=1).float().contiguous(), (wd @ be + b.detach().double()).float().contiguous()
+
+
 class _PackedBlock:
     def __init__(self, blk, D):
         validate_eva_block(blk)
@@ -276,6 +287,10 @@ class _PackedBlock:
             bias = lambda lin: lin.bias.detach().float() if lin.bias is not None else zeros
             bqkv = torch.cat([bias(at.q_proj), bias(at.k_proj), bias(at.v_proj)])
         self.wqkv, self.bqkv = ops.pack_weight(wqkv), bqkv.contiguous()
+        self.fold_block = FUSED_BLOCK_LN
+        if self.fold_block:
+            # LN(x) @ W^T + b = rstd * (x @ (W gamma)^T - mean * (W gamma) 1) + (W beta + b)
+            self.wqkv_f, self.cqkv, self.bqkv_f = _fold_ln(wqkv, bqkv, blk.norm1)
         self.wproj, self.bproj = ops.pack_weight(at.proj.weight), _f32(at.proj.bias)
         mlp = blk.mlp
         self.swiglu = hasattr(mlp, "fc1_g")
@@ -289,6 +304,8 @@ class _PackedBlock:
             b1[0:2 * Hd:2], b1[1:2 * Hd:2] = mlp.fc1_g.bias.detach().float(), mlp.fc1_x.bias.detach().float()
             self.hid, self.hp = Hd, Hp
             self.w1, self.bb1 = ops.pack_weight(w1), b1
+            if self.fold_block:
+                self.w1_f, self.c1, self.bb1_f = _fold_ln(w1, b1, blk.norm2)
             gpad = torch.zeros(Hp, dtype=torch.float32, device=dev)
             bpad = torch.zeros(Hp, dtype=torch.float32, device=dev)
             gpad[:Hd], bpad[:Hd] = mlp.norm.weight.detach().float(), mlp.norm.bias.detach().float()
@@ -308,6 +325,8 @@ class _PackedBlock:
         else:
             self.hid = mlp.fc1.out_features
             self.w1, self.bb1 = ops.pack_weight(mlp.fc1.weight), _f32(mlp.fc1.bias)
+            if self.fold_block:
+                self.w1_f, self.c1, self.bb1_f = _fold_ln(mlp.fc1.weight.detach().float(), mlp.fc1.bias.detach().float(), blk.norm2)
             self.w2, self.bb2 = ops.pack_weight(mlp.fc2.weight), _f32(mlp.fc2.bias)
 
 
@@ -321,6 +340,11 @@ class _PackedEncoder:
         self.tail = [(_f32(m.weight), _f32(m.bias), m.eps) for m in validate_transformer(enc.transformer)]
         self.blocks = [_PackedBlock(b, D) for b in enc.transformer.blocks]
         self.wout, self.bout = ops.pack_weight(enc.out_proj.weight), _f32(enc.out_proj.bias)
+        self.fold_block = FUSED_BLOCK_LN and len(self.tail) == 1 and all(b.fold_block for b in self.blocks)
+        if self.fold_block:
+            m = validate_transformer(enc.transformer)[0]
+            self.wout_f, self.cout, self.bout_f = _fold_ln(enc.out_proj.weight.detach().float(), enc.out_proj.bias.detach().float(), m)
+            self.eps_tail = m.eps
 
 
 def _attention_unfused(qkv: Split, att: Split, B: int, L: int, H: int, dh: int, D: int, dev):
@@ -350,15 +374,21 @@ def _attention_unfused(qkv: Split, att: Split, B: int, L: int, H: int, dh: int, 
     ops.gemm_raw(pa, va, o2, PASSES, 1)
 
 
-def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
-    """x fp32 [B*L, D], updated in place (pre-LN residual block, rope=None)."""
+def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int, fold=None):
+    """x fp32 [B*L, D], updated in place (pre-LN residual block, rope=None).
+    fold = (xs, st_in, st_mid, st_out): LayerNorm-free form - xs is the split-bf16 copy of x and st_in its row statistics
+    (both written by the GEMM that last produced x); proj refreshes xs + st_mid, fc2 refreshes xs + st_out."""
     dev = x.device
     M = B * L
     H, dh = pb.H, pb.dh
-    xn = Split(M, D, dev)
-    ops.layernorm(x, pb.g1, pb.b1, pb.eps1, out_split=xn)
     qkv = Split(M, 3 * D, dev)
-    ops.gemm(xn, pb.wqkv, bias=pb.bqkv, out_split=qkv, passes=PASSES)
+    if fold is not None:
+        xs, st_in, st_mid, st_out = fold
+        ops.gemm(xs, pb.wqkv_f, bias=pb.bqkv_f, out_split=qkv, passes=PASSES, ln_fold=(st_in, pb.cqkv, D, pb.eps1))
+    else:
+        xn = Split(M, D, dev)
+        ops.layernorm(x, pb.g1, pb.b1, pb.eps1, out_split=xn)
+        ops.gemm(xn, pb.wqkv, bias=pb.bqkv, out_split=qkv, passes=PASSES)
     att = Split(M, D, dev)
     if FUSED_ATTENTION and dh == 64 and (L <= 512 or FUSED_ATTENTION_LONG):
         # fused tcgen05 attention: S stays in tensor memory (L <= 512) or streams through a ring of TMEM slots in two
@@ -370,6 +400,11 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
     else:
         _attention_unfused(qkv, att, B, L, H, dh, D, dev)
     # x += proj(att)
+    if fold is not None:
+        # one writer per element (no split-K): the epilogue also emits split-bf16(x) and the row statistics for norm2
+        ops.gemm(att, pb.wproj, bias=pb.bproj, out_f32=x, resid=x, out_split=xs, stats_out=st_mid, passes=PASSES)
+        _run_mlp_folded(pb, x, xs, st_mid, st_out, M, D, dev)
+        return
     sk = _split_k_for(M, D, D)
     if sk > 1:
         ops.gemm(att, pb.wproj, bias=pb.bproj, out_f32=x, accumulate=True, split_k=sk, passes=PASSES)
@@ -400,6 +435,23 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int):
         ops.gemm(h, pb.w2, bias=pb.bb2, out_f32=x, resid=x, passes=PASSES, ln_fold=fold)
 
 
+def _run_mlp_folded(pb: _PackedBlock, x, xs, st_mid, st_out, M, D, dev):
+    """x += mlp(norm2(x)) with norm2 folded into fc1 (and SwiGLU.norm into fc2); fc2 refreshes xs and st_out."""
+    if pb.swiglu:
+        if not pb.fold_ln:
+            raise RuntimeError("PSAM_FUSED_BLOCK_LN requires PSAM_FUSED_INNER_LN")
+        stats = torch.zeros((M, 2), dtype=torch.float32, device=dev)
+        h = Split(M, pb.hp, dev, pitch=pb.hp)
+        ops.gemm(xs, pb.w1_f, bias=pb.bb1_f, out_split=h, passes=PASSES, swiglu=True, stats_out=stats,
+                 ln_fold=(st_mid, pb.c1, D, pb.eps2))
+        ops.gemm(h, pb.w2, bias=pb.bb2, out_f32=x, resid=x, out_split=xs, stats_out=st_out, passes=PASSES,
+                 ln_fold=(stats, pb.c2, pb.hid, pb.epsn))
+    else:
+        h = Split(M, pb.hid, dev)
+        ops.gemm(xs, pb.w1_f, bias=pb.bb1_f, out_split=h, act=ACT_GELU, passes=PASSES, ln_fold=(st_mid, pb.c1, D, pb.eps2))
+        ops.gemm(h, pb.w2, bias=pb.bb2, out_f32=x, resid=x, out_split=xs, stats_out=st_out, passes=PASSES)
+
+
 def run_pc_encoder(enc, coords, features):
     pk = _cached(enc, _PackedEncoder)
     patches = run_knn_grouper(enc.patch_embed.grouper, coords, features)
@@ -412,6 +464,19 @@ def run_pc_encoder(enc, coords, features):
     ops.gemm(embs, pk.wpp, bias=pk.bpp, out_f32=x, passes=PASSES)
     pos = Split(M, pk.wpos0.shape[0], dev)
     ops.small_in_linear(patches["centers"], pk.wpos0, pk.bpos0, None, None, 0.0, False, ACT_GELU, pos)
+    if pk.fold_block:
+        # LayerNorm-free encoder: every GEMM that writes the residual stream also writes its split-bf16 copy and row
+        # statistics; norm1 / norm2 / fc_norm are applied inside the consuming GEMMs' epilogues
+        nb = len(pk.blocks)
+        st = torch.zeros((2 * nb + 1, M, 2), dtype=torch.float32, device=dev)  # one memset for all statistics of the step
+        xs = Split(M, D, dev)
+        ops.gemm(pos, pk.wpos2, bias=pk.bpos2, out_f32=x, resid=x, out_split=xs, stats_out=st[0], passes=PASSES)
+        for i, pb in enumerate(pk.blocks):
+            _run_block(pb, x, B, L, D, fold=(xs, st[2 * i], st[2 * i + 1], st[2 * i + 2]))
+        out = torch.empty((B, L, enc.embed_dim), dtype=torch.float32, device=dev)
+        ops.gemm(xs, pk.wout_f, bias=pk.bout_f, out_f32=out.view(M, -1), passes=PASSES,
+                 ln_fold=(st[2 * nb], pk.cout, D, pk.eps_tail))
+        return out, patches
     ops.gemm(pos, pk.wpos2, bias=pk.bpos2, out_f32=x, resid=x, passes=PASSES)
     for pb in pk.blocks:
         _run_block(pb, x, B, L, D)

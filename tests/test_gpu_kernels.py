@@ -302,6 +302,67 @@ def test_gemm_tc_swiglu_stats_and_folded_layernorm():
         assert err < 1e-4 * max(1.0, float(want.abs().max())), (sk, err)
 
 
+def test_gemm_tc_layernorm_free_block_chain():
+    """The LayerNorm-free transformer block: a producer GEMM writes x (fp32 + split-bf16) and its row statistics; the
+    consumers apply norm1 / norm2 inside their epilogues with split-bf16, SwiGLU(+statistics) and GELU outputs.  Against
+    the unfused fp64 computation, with a row mean that is large against the spread (cancellation stress)."""
+    ops = _ops()
+    M, D, N1, Hd = 300, 256, 384, 344
+    Hp = (Hd + 63) // 64 * 64
+    eps = 1e-6
+    a0, w0, b0 = _rand(M, 128, seed=51), _rand(D, 128, seed=52, scale=128 ** -0.5), _rand(D, seed=53) + 3.0  # mean >> spread
+    r0 = _rand(M, D, seed=54)
+    g1, be1 = 1.0 + 0.2 * _rand(D, seed=55), 0.1 * _rand(D, seed=56)
+    x_want = r0.double() + a0.double() @ w0.double().t() + b0.double()
+    xn = torch.nn.functional.layer_norm(x_want, (D,), g1.double(), be1.double(), eps)
+
+    def fold(w, b):
+        wg = w.double() * g1.double()[None]
+        return ops.pack_weight(wg.float()), wg.sum(1).float().contiguous(), (w.double() @ be1.double() + b.double()).float().contiguous()
+
+    # producer: x = r0 + a0 @ w0^T + b0 -> fp32, split-bf16 and (sum, sum sq) per row
+    x = r0.clone()
+    xs = ops.Split(M, D, _dev())
+    st = torch.zeros(M, 2, device=_dev())
+    ops.gemm(ops.pack_weight(a0), ops.pack_weight(w0), bias=b0, out_f32=x, resid=x, out_split=xs, stats_out=st)
+    assert float((x - x_want.float()).abs().max()) < 5e-5 * float(x_want.abs().max())
+    assert float((xs.float() - x).abs().max()) < 3e-5 * float(x_want.abs().max())
+    torch.testing.assert_close(st[:, 0], x_want.sum(-1).float(), atol=2e-3, rtol=1e-5)
+    torch.testing.assert_close(st[:, 1], (x_want * x_want).sum(-1).float(), atol=2e-3, rtol=2e-5)
+    tol = lambda want: 2e-4 * max(1.0, float(want.abs().max()))
+    # consumer 1 (qkv form): split-bf16 output
+    w1, b1 = _rand(N1, D, seed=57, scale=D ** -0.5), _rand(N1, seed=58, scale=0.1)
+    W1f, c1, d1 = fold(w1, b1)
+    y = ops.Split(M, N1, _dev())
+    ops.gemm(xs, W1f, bias=d1, out_split=y, ln_fold=(st, c1, D, eps))
+    want = xn @ w1.double().t() + b1.double()
+    assert float((y.float() - want.float()).abs().max()) < tol(want)
+    # consumer 2 (EVA02 fc1 form): SwiGLU pairs + statistics of the products
+    wg_, wx_ = _rand(Hd, D, seed=59, scale=D ** -0.5), _rand(Hd, D, seed=60, scale=D ** -0.5)
+    bg_, bx_ = _rand(Hd, seed=61, scale=0.1), _rand(Hd, seed=62, scale=0.1)
+    wi, bi = torch.zeros(2 * Hp, D, device=_dev()), torch.zeros(2 * Hp, device=_dev())
+    wi[0:2 * Hd:2], wi[1:2 * Hd:2], bi[0:2 * Hd:2], bi[1:2 * Hd:2] = wg_, wx_, bg_, bx_
+    Wif, ci, di = fold(wi, bi)
+    hs = ops.Split(M, Hp, _dev(), pitch=Hp)
+    hst = torch.zeros(M, 2, device=_dev())
+    ops.gemm(xs, Wif, bias=di, out_split=hs, swiglu=True, stats_out=hst, ln_fold=(st, ci, D, eps))
+    h = torch.nn.functional.silu(xn @ wg_.double().t() + bg_.double()) * (xn @ wx_.double().t() + bx_.double())
+    assert float((hs.float()[:, :Hd] - h.float()).abs().max()) < tol(h)
+    assert float(hs.float()[:, Hd:].abs().max()) == 0.0
+    torch.testing.assert_close(hst[:, 0], h.sum(-1).float(), atol=5e-3, rtol=1e-4)
+    # consumer 3 (EVA-giant fc1 form): GELU + split-bf16 output; consumer 4 (out_proj form): fp32 output
+    y3 = ops.Split(M, N1, _dev())
+    ops.gemm(xs, W1f, bias=d1, out_split=y3, act=ops.ACT_GELU, ln_fold=(st, c1, D, eps))
+    want3 = torch.nn.functional.gelu(want)
+    assert float((y3.float() - want3.float()).abs().max()) < tol(want3)
+    y4 = torch.empty(M, N1, device=_dev())
+    ops.gemm(xs, W1f, bias=d1, out_f32=y4, ln_fold=(st, c1, D, eps))
+    assert float((y4 - want.float()).abs().max()) < tol(want)
+    # statistics of the output are refused where an element has more than one writer
+    with pytest.raises(RuntimeError):
+        ops.gemm(xs, W1f, bias=d1, out_f32=torch.zeros(M, N1, device=_dev()), accumulate=True, split_k=2, stats_out=st)
+
+
 def test_gemm_tc_batched_attention_shapes():
     """The batched operand views used by the ViT attention (heads = b1, clouds = b2)."""
     from psam_b200 import native as nv

@@ -31,11 +31,13 @@ def _report(name, got, want):
           f"range=[{float(want.min()):.3f},{float(want.max()):.3f}]")
 
 
-@pytest.mark.parametrize("name,fold_ln", [("tiny", True), ("tiny_fused_qkv", True), ("tiny", False)])
-def test_golden_end_to_end(golden_dir, name, fold_ln, monkeypatch):
+@pytest.mark.parametrize("name,fold_ln,fold_block", [("tiny", True, True), ("tiny_fused_qkv", True, True), ("tiny", True, False),
+                                                     ("tiny_fused_qkv", True, False), ("tiny", False, False)])
+def test_golden_end_to_end(golden_dir, name, fold_ln, fold_block, monkeypatch):
     from psam_b200 import engine
 
     monkeypatch.setattr(engine, "FUSED_INNER_LN", fold_ln)  # SwiGLU.norm folded into the GEMM epilogues / separate kernel
+    monkeypatch.setattr(engine, "FUSED_BLOCK_LN", fold_block)  # norm1 / norm2 / fc_norm folded (LayerNorm-free blocks) / kernels
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     B, N, G, K, P, seed = [int(v) for v in g["meta"]]
     model, oracle = _build(str(g["encoder"]), G, K, 1234 + seed)
