@@ -22,6 +22,7 @@ from .ops import ACT_GELU, ACT_NONE, ACT_RELU, Split
 
 FUSED_ATTENTION = True
 FUSED_ATTENTION_LONG = os.environ.get("PSAM_FUSED_ATTENTION_LONG", "1") != "0"
+ATTENTION_TWOPASS = os.environ.get("PSAM_ATTENTION_TWOPASS", "0") == "1"  # A/B: first-generation two-pass kernels
 FUSED_INNER_LN = os.environ.get("PSAM_FUSED_INNER_LN", "1") != "0"  # SwiGLU.norm folded into the fc1 / fc2 GEMM epilogues
 FUSED_MASK_DOT = os.environ.get("PSAM_FUSED_MASK_DOT", "1") != "0"
 # norm1 / norm2 / fc_norm folded into the qkv / fc1 / out_proj GEMMs: the producer of the residual stream (pos_embed, proj and
@@ -395,8 +396,9 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int, fold=N
         # sweeps (longer rows); V^T is read as an MN-major operand
         mk = lambda col: qkv.operand(rows=L, k=dh, col=col, nb1=H, b1_stride=dh, nb2=B, b2_stride=L * qkv.pitch)
         qa, ka, va = mk(0), mk(D), mk(2 * D)
-        nv.check(nv.lib().psam_attention_bf16x3(byref(qa), byref(ka), byref(va), att.ptr(), att.plane, att.pitch, dh,
-                                               L * att.pitch, dh ** -0.5, nv.stream()), "attention_bf16x3")
+        entry = nv.lib().psam_attention_bf16x3_twopass if ATTENTION_TWOPASS else nv.lib().psam_attention_bf16x3
+        nv.check(entry(byref(qa), byref(ka), byref(va), att.ptr(), att.plane, att.pitch, dh, L * att.pitch, dh ** -0.5,
+                       nv.stream()), "attention_bf16x3")
     else:
         _attention_unfused(qkv, att, B, L, H, dh, D, dev)
     # x += proj(att)

@@ -8,7 +8,7 @@ for p in (REPO, os.path.join(REPO, "point-sam_b200")):
 import torch  # noqa: E402
 from torch.profiler import ProfilerActivity, profile  # noqa: E402
 
-from oracle import synth  # noqa: E402
+from psam_b200 import synth  # noqa: E402
 from pc_sam.model import build_point_sam  # noqa: E402
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 4

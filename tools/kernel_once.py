@@ -1,5 +1,5 @@
 """Launch one hot kernel in isolation between cudaProfilerStart/Stop (for `ncu --profile-from-start off --set full`).
-usage: python tools/kernel_once.py {attention_long|attention|knn|knn_c4|border|gemm_qkv|gemm_pe}"""
+usage: python tools/kernel_once.py {attention_long|attention|knn|knn_c4|border|gemm_qkv|gemm_qkv_single|gemm_fc1|gemm_m2048|gemm_pe|fps}"""
 import os
 import sys
 from ctypes import byref
@@ -9,7 +9,7 @@ for p in (REPO, os.path.join(REPO, "point-sam_b200")):
     sys.path.insert(0, p)
 import torch  # noqa: E402
 
-from oracle import synth  # noqa: E402  (synthetic inputs only)
+from psam_b200 import synth  # noqa: E402
 from psam_b200 import native as nv, ops  # noqa: E402
 
 dev = torch.device("cuda:0")
@@ -43,18 +43,27 @@ def border(N):
     return lambda: ops.border_prompt(x, gt, pred, None, False)
 
 
-def gemm(M, N, K, hint):
+def gemm(M, N, K, hint, variant=0):
     a, w = ops.Split(M, K, dev), ops.Split(N, K, dev)
     a.t.normal_()
     w.t.normal_()
     out = torch.zeros(M, N, device=dev)
     ops.GEMM_TILE_HINT = hint
+    ops.GEMM_VARIANT = variant
     return lambda: ops.gemm(a, w, out_f32=out, passes=3)
+
+
+def fps(N, G=512):
+    xyz, _ = synth.make_batch(1, N, 5, "ball")
+    x = xyz.to(dev)
+    return lambda: ops.fps(x, G)
 
 
 fn = {"attention_long": lambda: attention(2048), "attention": lambda: attention(512), "knn": lambda: knn(32768, 512, 64, "ball"),
       "knn_c4": lambda: knn(131072, 2048, 256, "kitti"), "border": lambda: border(32768), "gemm_qkv": lambda: gemm(512, 3072, 1024, 1),
-      "gemm_pe": lambda: gemm(32768, 512, 128, 1)}[what]()
+      "gemm_pe": lambda: gemm(32768, 512, 128, 1),
+      "gemm_qkv_single": lambda: gemm(512, 3072, 1024, 1, ops.GV_NO_DUAL), "gemm_fc1": lambda: gemm(512, 5504, 1024, 1),
+      "gemm_m2048": lambda: gemm(2048, 3072, 1024, 1), "fps": lambda: fps(32768)}[what]()
 for _ in range(3):
     fn()
 torch.cuda.synchronize()

@@ -9,7 +9,7 @@ for p in (REPO, os.path.join(REPO, "point-sam_b200")):
 import torch  # noqa: E402
 
 from bench import CONFIGS  # noqa: E402
-from oracle import synth  # noqa: E402
+from psam_b200 import synth  # noqa: E402
 from pc_sam.model import build_point_sam  # noqa: E402
 
 ap = argparse.ArgumentParser()

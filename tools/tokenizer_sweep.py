@@ -9,7 +9,7 @@ for p in (REPO, os.path.join(REPO, "point-sam_b200")):
     sys.path.insert(0, p)
 import torch  # noqa: E402
 
-from oracle import synth  # noqa: E402
+from psam_b200 import synth  # noqa: E402
 from psam_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
