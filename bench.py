@@ -346,8 +346,11 @@ def run_c3(name, args, model, dev, dist, rank, world, barrier):
     enc, N, G, K, total, chunk, iters, M = C3[name]
     lo, hi = shard_range(total, rank, world)
     n_local = hi - lo
+    # clouds per CUDA graph: at most C3's 4, fewer when the rank's shard is small, so that `c3_lanes` graphs stay in flight on
+    # every rank count (8 ranks x 4 clouds: four 1-cloud graphs overlap instead of one 4-cloud graph running alone)
+    chunk = max(1, min(chunk, n_local // max(1, args.c3_lanes)))
     while chunk > 1 and n_local % chunk:
-        chunk //= 2
+        chunk -= 1
     n_chunks = n_local // max(1, chunk)
     saved = model.prompt_iters
     model.prompt_iters = iters
@@ -443,7 +446,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--depth", type=int, default=8, help="clouds in flight per GPU (independent streams/graphs)")
     ap.add_argument("--clouds-per-step", type=int, default=0, help="default: two rounds of the lanes (16 at depth 8)")
-    ap.add_argument("--c3-lanes", type=int, default=2, help="config c3: 4-cloud graphs in flight per GPU")
+    ap.add_argument("--c3-lanes", type=int, default=4, help="config c3: evaluation-loop graphs in flight per GPU")
     ap.add_argument("--no-c3", action="store_true", help="skip the sharded-batch evaluation-loop arm (config c3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the same-GPU PyTorch-eager reference timing")

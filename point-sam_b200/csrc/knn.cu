@@ -5,14 +5,9 @@
 // (:238-255).  The reference materialises the [B,G,N] distance matrix (64 MiB per cloud at
 // G=512,N=32768); here nothing but xyz is read and only the K winners are written.
 //
-// psam_knn_f32: one CTA per query centre.
-//   A. squared distances to a strided SAMPLE of the keys -> shared memory; exact K-th smallest of the
-//      sample by bitwise bisection -> tau, an upper bound of the true K-th distance.
-//   B. one pass over ALL keys (xyz streamed from L2), candidates with d2 <= tau appended to a
-//      shared-memory list (warp-aggregated).  Expected size ~K*stride; if the list overflows
-//      (adversarial duplicates) the kernel falls back to exact bisection over the whole key set.
-//   C. exact K-th among the candidates by bisection; ties at the K-th distance resolved by lower key
-//      index; output sorted by (distance, index) so the result is deterministic.
+// psam_knn_f32: one CTA per group of 1 / 2 / 4 query centres (see knn_kernel): sample bound -> one branch-free sweep of all
+// keys recording hit bits in registers -> exact re-test of the hits -> exact K-th by radix select, ties by lower key
+// index, output sorted by (distance, index) so the result is deterministic.
 // Distances are the direct-difference form fmaf(dz,dz,fmaf(dy,dy,dx*dx)) (exact for coincident points).
 #include "psam_common.cuh"
 #include "../../include/psam_b200.h"
@@ -101,194 +96,279 @@ __device__ uint32_t kth_smallest_radix(const float* vals, int n, int k, int* his
     return prefix;
 }
 
+// One CTA serves C consecutive query centres of one cloud.
+//   A. per centre: squared distances to a strided SAMPLE of the keys -> exact K-th smallest of the sample (radix select)
+//      = tau_c, an upper bound of the true K-th distance.
+//   B. ONE sweep over all keys for the C centres together (each 128-bit key load feeds 4 x C pair tests).  The test is a
+//      3-FMA filter |p|^2 + |c|^2 - 2 p.c, biased low by 2e-6 (|p|^2 + |c|^2) so that it can only over-accept; hits are only
+//      recorded as one bit per (point, centre) in registers - no branch, no shared-memory traffic in the hot loop
+//      (round 1 branched into a shared-memory append for every point: 45 of its 61 thread-instructions per pair).
+//      After each super-tile of 32 quads per thread the set bits are revisited: exact direct-difference distance
+//      (bit-identical to the oracle), exact test against tau_c, append to the centre's candidate list.
+//   C. per centre: exact K-th among the candidates, ties at the K-th distance by lower key index, output sorted by
+//      (distance, index).  Candidate overflow (adversarial duplicates) falls back to exact bisection over all keys.
+template <int C>
+struct KnnSmem {
+    float* s_sample;  // [sample_cap] (>= 2K); reused as the final list of each centre
+    float* c_d2;      // [C][cap]
+    int* c_idx;       // [C][cap]
+    int* cnt;         // [64]
+    int* hist;        // [KNN_HIST]
+};
+
+constexpr int KNN_TILE_QUADS = 32;  // quads (4 keys) per thread and super-tile: 4 x 32 hit bits = 4 registers per centre
+
+template <int C>
 __global__ void __launch_bounds__(KNN_THREADS)
 knn_kernel(const float* __restrict__ query, const float* __restrict__ key, int Q, int N, int K, int sample_stride,
            int sample_cap, int cap, long long* __restrict__ idx_out, float* __restrict__ d2_out) {
     pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_sample = reinterpret_cast<float*>(smem_raw);  // [sample_cap] (>= 2K); reused as the final list
-    float* c_d2 = s_sample + sample_cap;                   // [cap]
-    int* c_idx = reinterpret_cast<int*>(c_d2 + cap);       // [cap]
-    int* cnt = c_idx + cap;                                // [64]
-    int* hist = cnt + 64;                                  // [KNN_HIST] radix-select histogram
-    __shared__ int s_ncand, s_overflow, s_nsel;
+    float* s_sample = reinterpret_cast<float*>(smem_raw);       // [sample_cap]
+    float* c_d2_all = s_sample + sample_cap;                    // [C][cap]
+    int* c_idx_all = reinterpret_cast<int*>(c_d2_all + (size_t)C * cap);  // [C][cap]
+    int* cnt = c_idx_all + (size_t)C * cap;                     // [64]
+    int* hist = cnt + 64;                                       // [KNN_HIST]
+    __shared__ int s_ncand[C], s_overflow[C], s_nsel;
+    __shared__ uint32_t s_tau[C];
     __shared__ int s_wcnt[KNN_THREADS / 32];
 
-    const int b = blockIdx.y, q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.y, q0 = blockIdx.x * C, tid = threadIdx.x, lane = tid & 31;
     key += (size_t)b * N * 3;
-    const float* pq = query + ((size_t)b * Q + q) * 3;
-    const float cx = pq[0], cy = pq[1], cz = pq[2];
-
-    if (tid == 0) s_ncand = 0, s_overflow = 0, s_nsel = 0;
+    float cx[C], cy[C], cz[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const int q = min(q0 + c, Q - 1);  // a ragged last group recomputes the last centre (results not stored twice)
+        const float* pq = query + ((size_t)b * Q + q) * 3;
+        cx[c] = pq[0], cy[c] = pq[1], cz[c] = pq[2];
+    }
+    if (tid < C) s_ncand[tid] = 0, s_overflow[tid] = 0;
+    if (tid == 0) s_nsel = 0;
     zero_counters(cnt);
 
-    // ---- A. sample bound ---------------------------------------------------------------------
+    // ---- A. sample bound per centre ------------------------------------------------------------
     const int ns = (N + sample_stride - 1) / sample_stride;
-    for (int i = tid; i < ns; i += KNN_THREADS) {
-        const size_t j = (size_t)i * sample_stride;
-        s_sample[i] = sqdist3(key[j * 3], key[j * 3 + 1], key[j * 3 + 2], cx, cy, cz);
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+        for (int i = tid; i < ns; i += KNN_THREADS) {
+            const size_t j = (size_t)i * sample_stride;
+            s_sample[i] = sqdist3(key[j * 3], key[j * 3 + 1], key[j * 3 + 2], cx[c], cy[c], cz[c]);
+        }
+        __syncthreads();
+        const uint32_t t = kth_smallest_radix(s_sample, ns, K, hist);
+        if (tid == 0) s_tau[c] = t;
+        __syncthreads();
     }
-    __syncthreads();
-    uint32_t tau = kth_smallest_radix(s_sample, ns, K, hist);
+    uint32_t tau[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) tau[c] = s_tau[c];
 
-    // ---- B. collect candidates d2 <= tau -------------------------------------------------------
-    // Four consecutive points per thread and step, fetched as three coalesced 128-bit loads (12 floats): 4x fewer load
-    // instructions than point-wise access and all of them independent, so the sweep is no longer latency-bound.
-    // Hits are rare (about K * sample_stride of N points): one shared-memory atomic per hit is cheaper than a
-    // warp-aggregated append whose vote / popc / shuffle sequence every lane would execute for every point.
-    auto append = [&](bool hit, float d, int j) {
-        if (hit) {
-            const int pos = atomicAdd(&s_ncand, 1);
-            if (pos < cap) {
-                c_d2[pos] = d;
-                c_idx[pos] = j;
-            } else {
-                s_overflow = 1;
-            }
+    auto append = [&](int c, float d, int j) {
+        const int pos = atomicAdd(&s_ncand[c], 1);
+        if (pos < cap) {
+            c_d2_all[(size_t)c * cap + pos] = d;
+            c_idx_all[(size_t)c * cap + pos] = j;
+        } else {
+            s_overflow[c] = 1;
         }
     };
+
+    // ---- B. the sweep ----------------------------------------------------------------------------
     int n_vec = 0;
     if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(key) & 15) == 0) {
         n_vec = N;
         const float4* key4 = reinterpret_cast<const float4*>(key);
         const int nquad = N >> 2;
-        for (int q0 = 0; q0 < nquad; q0 += KNN_THREADS) {
-            const int qd = q0 + tid;
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
-            const bool valid = qd < nquad;
-            if (valid) {
-                const float4 a = key4[(size_t)qd * 3], bq = key4[(size_t)qd * 3 + 1], c = key4[(size_t)qd * 3 + 2];
-                d[0] = sqdist3(a.x, a.y, a.z, cx, cy, cz);
-                d[1] = sqdist3(a.w, bq.x, bq.y, cx, cy, cz);
-                d[2] = sqdist3(bq.z, bq.w, c.x, cx, cy, cz);
-                d[3] = sqdist3(c.y, c.z, c.w, cx, cy, cz);
-            }
+        constexpr float SHRINK = 1.0f - 2e-6f;  // the filter may only over-accept: bias the positive part low
+        float m2x[C], m2y[C], m2z[C], cn[C], tauf[C];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) append(valid && __float_as_uint(d[u]) <= tau, d[u], qd * 4 + u);
+        for (int c = 0; c < C; ++c) {
+            m2x[c] = -2.0f * cx[c], m2y[c] = -2.0f * cy[c], m2z[c] = -2.0f * cz[c];
+            cn[c] = fmaf(cz[c], cz[c], fmaf(cy[c], cy[c], cx[c] * cx[c])) * SHRINK;
+            tauf[c] = __uint_as_float(tau[c]);
         }
-    }
-    for (int j0 = n_vec; j0 < N; j0 += KNN_THREADS) {
-        const int j = j0 + tid;
-        float d = 0.f;
-        bool hit = false;
-        if (j < N) {
-            d = sqdist3(key[(size_t)j * 3], key[(size_t)j * 3 + 1], key[(size_t)j * 3 + 2], cx, cy, cz);
-            hit = __float_as_uint(d) <= tau;
-        }
-        append(hit, d, j);
-    }
-    __syncthreads();
-
-    int ncand = s_ncand;
-    if (s_overflow) {
-        // ---- fallback: exact bisection over the whole key set (distances recomputed per pass) ----
-        uint32_t res = 0;
-        for (int bit = 30; bit >= 0; --bit) {
-            const uint32_t cand = res | (1u << bit);
-            int c = 0;
-            for (int j = tid; j < N; j += KNN_THREADS)
-                c += (__float_as_uint(sqdist3(key[(size_t)j * 3], key[(size_t)j * 3 + 1], key[(size_t)j * 3 + 2], cx, cy, cz)) < cand);
-            if (block_count(c, &cnt[bit]) < K) res = cand;
-        }
-        zero_counters(cnt);
-        if (tid == 0) s_ncand = 0;
-        __syncthreads();
-        tau = res;  // the exact K-th distance
-        // strictly-below first (fewer than K of them), then ties in ascending key index until full
-        for (int pass = 0; pass < 2; ++pass) {
-            for (int j0 = 0; j0 < N; j0 += KNN_THREADS) {
-                const int j = j0 + tid;
-                float d = 0.f;
-                bool hit = false;
-                if (j < N) {
-                    d = sqdist3(key[(size_t)j * 3], key[(size_t)j * 3 + 1], key[(size_t)j * 3 + 2], cx, cy, cz);
-                    const uint32_t u = __float_as_uint(d);
-                    hit = pass == 0 ? (u < tau) : (u == tau);
-                }
-                const uint32_t m = __ballot_sync(0xffffffffu, hit);
-                if (lane == 0) s_wcnt[tid >> 5] = __popc(m);
-                __syncthreads();
-                int base = s_ncand;
-                for (int w = 0; w < (tid >> 5); ++w) base += s_wcnt[w];
-                if (hit) {
-                    const int pos = base + __popc(m & ((1u << lane) - 1u));
-                    if (pos < cap) {
-                        c_d2[pos] = d;
-                        c_idx[pos] = j;
+        for (int qt = 0; qt < nquad; qt += KNN_TILE_QUADS * KNN_THREADS) {
+            uint32_t bits[C][4];
+#pragma unroll
+            for (int c = 0; c < C; ++c) bits[c][0] = bits[c][1] = bits[c][2] = bits[c][3] = 0u;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+#pragma unroll
+                for (int i8 = 0; i8 < 8; ++i8) {
+                    const int qd = qt + (w * 8 + i8) * KNN_THREADS + tid;
+                    if (qd < nquad) {
+                        const float4 a = key4[(size_t)qd * 3], bq = key4[(size_t)qd * 3 + 1], cq = key4[(size_t)qd * 3 + 2];
+                        const float px[4] = {a.x, a.w, bq.z, cq.y}, py[4] = {a.y, bq.x, bq.w, cq.z}, pz[4] = {a.z, bq.y, cq.x, cq.w};
+                        float pn[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) pn[u] = fmaf(pz[u], pz[u], fmaf(py[u], py[u], px[u] * px[u])) * SHRINK;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            uint32_t m = 0u;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float f = fmaf(px[u], m2x[c], fmaf(py[u], m2y[c], fmaf(pz[u], m2z[c], pn[u] + cn[c])));
+                                m |= (f <= tauf[c]) ? (1u << u) : 0u;
+                            }
+                            bits[c][w] |= m << (i8 * 4);
+                        }
                     }
                 }
-                __syncthreads();
-                if (tid == 0) {
-                    int tot = 0;
-                    for (int w = 0; w < KNN_THREADS / 32; ++w) tot += s_wcnt[w];
-                    s_ncand = min(s_ncand + tot, cap);
+            }
+            // revisit the recorded hits: exact distance, exact test, append
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    uint32_t m = bits[c][w];
+                    while (m) {
+                        const int bpos = __ffs(m) - 1;
+                        m &= m - 1u;
+                        const int it = w * 8 + (bpos >> 2);
+                        const int j = (qt + it * KNN_THREADS + tid) * 4 + (bpos & 3);
+                        const float d = sqdist3(key[(size_t)j * 3], key[(size_t)j * 3 + 1], key[(size_t)j * 3 + 2], cx[c], cy[c], cz[c]);
+                        if (__float_as_uint(d) <= tau[c]) append(c, d, j);
+                    }
                 }
-                __syncthreads();
-                if (s_ncand >= cap) break;
             }
         }
-        ncand = s_ncand;
     }
+    for (int j0 = n_vec; j0 < N; j0 += KNN_THREADS) {  // unaligned / ragged clouds: plain point-wise sweep
+        const int j = j0 + tid;
+        if (j < N) {
+            const float x = key[(size_t)j * 3], y = key[(size_t)j * 3 + 1], z = key[(size_t)j * 3 + 2];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float d = sqdist3(x, y, z, cx[c], cy[c], cz[c]);
+                if (__float_as_uint(d) <= tau[c]) append(c, d, j);
+            }
+        }
+    }
+    __syncthreads();
 
-    // ---- C. exact K-th among candidates; ties at the K-th distance by lower key index -----------
-    const uint32_t kth = kth_smallest_radix(c_d2, ncand, K, hist);
-    int c_lt = 0, c_le = 0;
-    for (int i = tid; i < ncand; i += KNN_THREADS) {
-        const uint32_t u = __float_as_uint(c_d2[i]);
-        c_lt += (u < kth);
-        c_le += (u <= kth);
-    }
-    c_lt = block_count(c_lt, &cnt[32]);
-    c_le = block_count(c_le, &cnt[33]);
-    uint32_t idx_thr = 0xFFFFFFFFu;  // keep ties with index <= idx_thr
-    if (c_le > K) {
-        const int need = K - c_lt;  // >= 1
-        uint32_t res = 0;           // `need`-th smallest index among the ties
-        for (int bit = 30; bit >= 0; --bit) {
-            const uint32_t cand = res | (1u << bit);
-            int c = 0;
-            for (int i = tid; i < ncand; i += KNN_THREADS)
-                c += (__float_as_uint(c_d2[i]) == kth && (uint32_t)c_idx[i] < cand);
-            if (block_count(c, &cnt[bit]) < need) res = cand;
+    // ---- per centre: overflow fallback, then C ------------------------------------------------------
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+        if (q0 + c >= Q) break;  // uniform
+        const int q = q0 + c;
+        float* c_d2 = c_d2_all + (size_t)c * cap;
+        int* c_idx = c_idx_all + (size_t)c * cap;
+        const float ccx = cx[c], ccy = cy[c], ccz = cz[c];
+        int ncand = min(s_ncand[c], cap);
+        if (s_overflow[c]) {
+            // ---- fallback: exact bisection over the whole key set (distances recomputed per pass) ----
+            zero_counters(cnt);
+            uint32_t res = 0;
+            for (int bit = 30; bit >= 0; --bit) {
+                const uint32_t cand = res | (1u << bit);
+                int n = 0;
+                for (int j = tid; j < N; j += KNN_THREADS)
+                    n += (__float_as_uint(sqdist3(key[(size_t)j * 3], key[(size_t)j * 3 + 1], key[(size_t)j * 3 + 2], ccx, ccy, ccz)) < cand);
+                if (block_count(n, &cnt[bit]) < K) res = cand;
+            }
+            __syncthreads();
+            if (tid == 0) s_ncand[c] = 0;
+            __syncthreads();
+            const uint32_t tx = res;  // the exact K-th distance
+            // strictly-below first (fewer than K of them), then ties in ascending key index until full
+            for (int pass = 0; pass < 2; ++pass) {
+                for (int j0 = 0; j0 < N; j0 += KNN_THREADS) {
+                    const int j = j0 + tid;
+                    float d = 0.f;
+                    bool hit = false;
+                    if (j < N) {
+                        d = sqdist3(key[(size_t)j * 3], key[(size_t)j * 3 + 1], key[(size_t)j * 3 + 2], ccx, ccy, ccz);
+                        const uint32_t u = __float_as_uint(d);
+                        hit = pass == 0 ? (u < tx) : (u == tx);
+                    }
+                    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                    if (lane == 0) s_wcnt[tid >> 5] = __popc(m);
+                    __syncthreads();
+                    int base = s_ncand[c];
+                    for (int w = 0; w < (tid >> 5); ++w) base += s_wcnt[w];
+                    if (hit) {
+                        const int pos = base + __popc(m & ((1u << lane) - 1u));
+                        if (pos < cap) {
+                            c_d2[pos] = d;
+                            c_idx[pos] = j;
+                        }
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        int tot = 0;
+                        for (int w = 0; w < KNN_THREADS / 32; ++w) tot += s_wcnt[w];
+                        s_ncand[c] = min(s_ncand[c] + tot, cap);
+                    }
+                    __syncthreads();
+                    if (s_ncand[c] >= cap) break;
+                }
+            }
+            ncand = s_ncand[c];
         }
-        idx_thr = res;
-    }
-    __syncthreads();
-    // compact the K winners into the (now free) sample area, then order them by (d2, index)
-    float* f_d2 = s_sample;
-    int* f_idx = reinterpret_cast<int*>(s_sample + K);
-    for (int i0 = 0; i0 < ncand; i0 += KNN_THREADS) {
-        const int i = i0 + tid;
-        bool hit = false;
-        if (i < ncand) {
+
+        // ---- C. exact K-th among candidates; ties at the K-th distance by lower key index -----------
+        zero_counters(cnt);
+        if (tid == 0) s_nsel = 0;
+        const uint32_t kth = kth_smallest_radix(c_d2, ncand, K, hist);
+        int c_lt = 0, c_le = 0;
+        for (int i = tid; i < ncand; i += KNN_THREADS) {
             const uint32_t u = __float_as_uint(c_d2[i]);
-            hit = (u < kth) || (u == kth && (uint32_t)c_idx[i] <= idx_thr);
+            c_lt += (u < kth);
+            c_le += (u <= kth);
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_nsel, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (hit) {
-                const int pos = base + __popc(m & ((1u << lane) - 1u));
-                if (pos < K) {
-                    f_d2[pos] = c_d2[i];
-                    f_idx[pos] = c_idx[i];
+        c_lt = block_count(c_lt, &cnt[32]);
+        c_le = block_count(c_le, &cnt[33]);
+        uint32_t idx_thr = 0xFFFFFFFFu;  // keep ties with index <= idx_thr
+        if (c_le > K) {
+            const int need = K - c_lt;  // >= 1
+            uint32_t res = 0;           // `need`-th smallest index among the ties
+            for (int bit = 30; bit >= 0; --bit) {
+                const uint32_t cand = res | (1u << bit);
+                int n = 0;
+                for (int i = tid; i < ncand; i += KNN_THREADS)
+                    n += (__float_as_uint(c_d2[i]) == kth && (uint32_t)c_idx[i] < cand);
+                if (block_count(n, &cnt[bit]) < need) res = cand;
+            }
+            idx_thr = res;
+        }
+        __syncthreads();
+        // compact the K winners into the sample area (free after phase A), then order them by (d2, index)
+        float* f_d2 = s_sample;
+        int* f_idx = reinterpret_cast<int*>(s_sample + K);
+        for (int i0 = 0; i0 < ncand; i0 += KNN_THREADS) {
+            const int i = i0 + tid;
+            bool hit = false;
+            if (i < ncand) {
+                const uint32_t u = __float_as_uint(c_d2[i]);
+                hit = (u < kth) || (u == kth && (uint32_t)c_idx[i] <= idx_thr);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nsel, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (hit) {
+                    const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (pos < K) {
+                        f_d2[pos] = c_d2[i];
+                        f_idx[pos] = c_idx[i];
+                    }
                 }
             }
         }
-    }
-    __syncthreads();
-    for (int i = tid; i < K; i += KNN_THREADS) {
-        const uint32_t u = __float_as_uint(f_d2[i]);
-        const int ji = f_idx[i];
-        int rank = 0;
-        for (int t = 0; t < K; ++t) {
-            const uint32_t ut = __float_as_uint(f_d2[t]);
-            rank += (ut < u) || (ut == u && f_idx[t] < ji);
+        __syncthreads();
+        for (int i = tid; i < K; i += KNN_THREADS) {
+            const uint32_t u = __float_as_uint(f_d2[i]);
+            const int ji = f_idx[i];
+            int rank = 0;
+            for (int t = 0; t < K; ++t) {
+                const uint32_t ut = __float_as_uint(f_d2[t]);
+                rank += (ut < u) || (ut == u && f_idx[t] < ji);
+            }
+            idx_out[((size_t)b * Q + q) * K + rank] = ji;
+            if (d2_out) d2_out[((size_t)b * Q + q) * K + rank] = f_d2[i];
         }
-        idx_out[((size_t)b * Q + q) * K + rank] = ji;
-        if (d2_out) d2_out[((size_t)b * Q + q) * K + rank] = f_d2[i];
+        __syncthreads();  // f_d2 / f_idx (the sample area) are reused by the next centre
     }
 }
 
@@ -608,9 +688,23 @@ extern "C" int psam_knn_f32(const float* query, const float* key, int B, int Q, 
     if (cap > KNN_MAX_CAP) cap = KNN_MAX_CAP;
     if (cap > N) cap = (N + 3) & ~3;  // cannot hold more candidates than keys
     if (cap < K) return PSAM_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)sample_cap * 4 + (size_t)cap * 8 + (64 + KNN_HIST) * 4;
-    PSAM_CUDA_TRY(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PSAM_CUDA_TRY(psam::launch(knn_kernel, dim3(dim3(Q, B)), dim3(KNN_THREADS), (size_t)(smem), stream, query, key, Q, N, K, stride, sample_cap, (int)cap, idx_out, d2_out));
+    // centres per CTA: as many as keep >= 1.5 CTAs per SM (the per-centre select phases are latency-bound: they need
+    // co-resident CTAs to overlap) and fit two CTAs' shared memory on an SM
+    auto smem_for = [&](int c) { return (size_t)sample_cap * 4 + (size_t)c * cap * 8 + (64 + KNN_HIST) * 4; };
+    int C = 4;
+    while (C > 1 && ((long long)B * ((Q + C - 1) / C) < 222 || smem_for(C) > 100 * 1024)) C /= 2;
+    const size_t smem = smem_for(C);
+    const dim3 grid((unsigned)((Q + C - 1) / C), (unsigned)B);
+#define PSAM_KNN_LAUNCH(CC)                                                                                                  \
+    do {                                                                                                                     \
+        PSAM_CUDA_TRY(cudaFuncSetAttribute(knn_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        PSAM_CUDA_TRY(psam::launch(knn_kernel<CC>, grid, dim3(KNN_THREADS), smem, stream, query, key, Q, N, K, stride,      \
+                                   sample_cap, (int)cap, idx_out, d2_out));                                                 \
+    } while (0)
+    if (C == 4) PSAM_KNN_LAUNCH(4);
+    else if (C == 2) PSAM_KNN_LAUNCH(2);
+    else PSAM_KNN_LAUNCH(1);
+#undef PSAM_KNN_LAUNCH
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
