@@ -795,6 +795,10 @@ attention_flow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             xb[sub * 128 + r] = bm;
             asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 softmax warps; also: both threads of a row hold their S in registers
             bm = fmaxf(bm, xb[(sub ^ 1) * 128 + r]);
+            // pv_done completes one phase per PV_j.  A parity wait can only tell the current phase from the preceding one, so
+            // every thread observes the phases strictly in order: phase j-1 exactly once during block j - here if O must
+            // be rescaled, otherwise at the end of the block (by then PV_{j-1} has normally retired: no stall).
+            bool waited_pv = false;
             if (j == 0) {
                 mref = bm;
             } else {
@@ -802,6 +806,7 @@ attention_flow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 if (__any_sync(0xffffffffu, need)) {
                     // slow path: move the reference and rescale what has been accumulated under the old one
                     mbar_wait(smem_u32(&pv_done), (uint32_t)(j - 1) & 1u);
+                    waited_pv = true;
                     tc_fence_after();
                     const float f = need ? ex2f((mref - bm) * c) : 1.0f;
                     uint32_t o[32];
@@ -837,6 +842,7 @@ attention_flow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 tmem_st_32x16(t_slot + (uint32_t)(sub * 32 + hh * 16), hi);
                 tmem_st_32x16(t_slot + 64u + (uint32_t)(sub * 32 + hh * 16), lo);
             }
+            if (j > 0 && !waited_pv) mbar_wait(smem_u32(&pv_done), (uint32_t)(j - 1) & 1u);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(smem_u32(&p_full[slot]));
