@@ -159,6 +159,10 @@ int psam_attention_bf16x3_twopass(const psam_operand* q, const psam_operand* k, 
                                   long long out_plane, long long ldo, long long out_head_stride,
                                   long long out_cloud_stride, float scale, cudaStream_t stream);
 
+/* y = split-bf16(x (+ add)) with zero fill up to `pitch` (add may be NULL; same row stride as x). */
+int psam_split_add_f32(const float* x, const float* add, long long ld, long long rows, int D, void* y_hi, long long y_plane,
+                       long long ldy_s, long long pitch, cudaStream_t stream);
+
 /* Small fp32 SIMT linear for the prompt decoder (rows < one MMA tile):
  * Y[z][M,N] = act((X[z] (+X2[z]))[M,K] * W[z][N,K]^T + b[z]) (+R[z]); strides in elements; any pointer
  * stride may be 0 to broadcast.  Replaces nn.Linear in transformer.py:199-202,239-253 and the MLP
@@ -191,6 +195,8 @@ typedef struct {
     int padded;                               /* 1: x rows (zeros), gamma, beta and outputs are valid up to roundup4(D) */
     int policy;                               /* 0: lowest latency (CTA per row for short token streams); 1: least SM-time
                                                * (warp per row, no block barriers) - used when several clouds are in flight */
+    const float* post_add; long long ld_post; /* optional: a SECOND split-bf16 output y2 = split(y + post_add[row]) - the     */
+    void* y2_hi; long long y2_plane, ldy2_s;  /* "keys + positional encoding" operand of the decoder's projections         */
 } psam_ln_args;
 int psam_layernorm_f32(const psam_ln_args* args, cudaStream_t stream);
 

@@ -51,6 +51,7 @@ __device__ __forceinline__ void ln_store(const psam_ln_args& a, long long row, i
     v = apply_act(v, a.act);
     if (a.y) a.y[row * a.ldy + c] = v;
     if (a.y_hi) store_split((__nv_bfloat16*)a.y_hi, a.y_plane, row * a.ldy_s + c, v);
+    if (a.y2_hi) store_split((__nv_bfloat16*)a.y2_hi, a.y2_plane, row * a.ldy2_s + c, v + a.post_add[row * a.ld_post + c]);
 }
 
 template <int VPL>  // values per lane, D <= 32*VPL
@@ -148,6 +149,17 @@ __device__ __forceinline__ void ln_store4(const psam_ln_args& a, long long row, 
         __nv_bfloat16* p = (__nv_bfloat16*)a.y_hi + row * a.ldy_s + c;
         *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
         *reinterpret_cast<uint2*>(p + a.y_plane) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    }
+    if (a.y2_hi) {
+        const float4 t = *reinterpret_cast<const float4*>(a.post_add + row * a.ld_post + c);
+        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(v.x + t.x, h0, l0);
+        split_bf16(v.y + t.y, h1, l1);
+        split_bf16(v.z + t.z, h2, l2);
+        split_bf16(v.w + t.w, h3, l3);
+        __nv_bfloat16* p = (__nv_bfloat16*)a.y2_hi + row * a.ldy2_s + c;
+        *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+        *reinterpret_cast<uint2*>(p + a.y2_plane) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
     }
 }
 
@@ -587,14 +599,16 @@ __global__ void add_bcast_kernel(const float* __restrict__ a, const float* __res
     }
 }
 
-__global__ void split_f32_kernel(const float* __restrict__ x, long long ld, long long rows, int D, __nv_bfloat16* __restrict__ yh,
-                                 long long y_plane, long long ldy_s, long long pitch) {
+__global__ void split_f32_kernel(const float* __restrict__ x, const float* __restrict__ add, long long ld, long long rows, int D,
+                                 __nv_bfloat16* __restrict__ yh, long long y_plane, long long ldy_s, long long pitch) {
     pdl_prologue();
     const long long total = rows * pitch;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / pitch;
         const int c = (int)(i % pitch);
-        store_split(yh, y_plane, r * ldy_s + c, c < D ? x[r * ld + c] : 0.f);
+        float v = c < D ? x[r * ld + c] : 0.f;
+        if (add && c < D) v += add[r * ld + c];
+        store_split(yh, y_plane, r * ldy_s + c, v);
     }
 }
 
@@ -862,6 +876,7 @@ using namespace psam;
 extern "C" int psam_layernorm_f32(const psam_ln_args* a, cudaStream_t stream) {
     if (!a || !a->x || !a->gamma || !a->beta || a->rows <= 0 || a->D <= 0 || (!a->y && !a->y_hi)) return PSAM_ERR_ARG;
     if (a->gbias && a->group_rows <= 0) return PSAM_ERR_ARG;
+    if (a->y2_hi && !a->post_add) return PSAM_ERR_ARG;
     if (a->D > 4096) return PSAM_ERR_UNSUPPORTED;
     // Short token streams (512 rows of the ViT): a CTA per row finishes sooner (latency policy), a warp per row costs fewer
     // SM-cycles (throughput policy, several clouds in flight): +1.2 % clouds/s at depth 8, +0.3 ms single-stream.
@@ -870,7 +885,9 @@ extern "C" int psam_layernorm_f32(const psam_ln_args* a, cudaStream_t stream) {
     const bool vec = (a->D % 4 == 0 || a->padded) && a->ldx % 4 == 0 && al(a->x) && al(a->gamma) && al(a->beta) &&
                      (!a->r || (a->ldr % 4 == 0 && al(a->r))) && (!a->gbias || (a->ld_gbias % 4 == 0 && al(a->gbias))) &&
                      (!a->y || (a->ldy % 4 == 0 && al(a->y))) &&
-                     (!a->y_hi || (a->ldy_s % 4 == 0 && a->y_plane % 4 == 0 && ((uintptr_t)a->y_hi & 7) == 0));
+                     (!a->y_hi || (a->ldy_s % 4 == 0 && a->y_plane % 4 == 0 && ((uintptr_t)a->y_hi & 7) == 0)) &&
+                     (!a->y2_hi || (a->ldy2_s % 4 == 0 && a->y2_plane % 4 == 0 && ((uintptr_t)a->y2_hi & 7) == 0 &&
+                                    a->ld_post % 4 == 0 && al(a->post_add)));
     if (block_per_row && vec) {
         const int nv = ceil_div(a->D, 1024);
         if (nv <= 1) PSAM_CUDA_TRY(psam::launch(layernorm_block_v4_kernel<1>, dim3(a->rows), dim3(256), (size_t)0, stream, *a));
@@ -1065,7 +1082,15 @@ extern "C" int psam_add_bcast_f32(const float* a, const float* b, long long n, l
 extern "C" int psam_split_f32(const float* x, long long ld, long long rows, int D, void* y_hi, long long y_plane,
                               long long ldy_s, long long pitch, cudaStream_t stream) {
     if (!x || !y_hi || rows <= 0 || D <= 0 || pitch < D) return PSAM_ERR_ARG;
-    PSAM_CUDA_TRY(psam::launch(split_f32_kernel, dim3(grid_for(rows * pitch, 256)), dim3(256), (size_t)(0), stream, x, ld, rows, D, (__nv_bfloat16*)y_hi, y_plane, ldy_s, pitch));
+    PSAM_CUDA_TRY(psam::launch(split_f32_kernel, dim3(grid_for(rows * pitch, 256)), dim3(256), (size_t)(0), stream, x, (const float*)nullptr, ld, rows, D, (__nv_bfloat16*)y_hi, y_plane, ldy_s, pitch));
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_split_add_f32(const float* x, const float* add, long long ld, long long rows, int D, void* y_hi, long long y_plane,
+                                  long long ldy_s, long long pitch, cudaStream_t stream) {
+    if (!x || !y_hi || rows <= 0 || D <= 0 || pitch < D) return PSAM_ERR_ARG;
+    PSAM_CUDA_TRY(psam::launch(split_f32_kernel, dim3(grid_for(rows * pitch, 256)), dim3(256), (size_t)(0), stream, x, add, ld, rows, D, (__nv_bfloat16*)y_hi, y_plane, ldy_s, pitch));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }

@@ -25,6 +25,9 @@ FUSED_ATTENTION_LONG = os.environ.get("PSAM_FUSED_ATTENTION_LONG", "1") != "0"
 ATTENTION_TWOPASS = os.environ.get("PSAM_ATTENTION_TWOPASS", "0") == "1"  # A/B: first-generation two-pass kernels
 FUSED_INNER_LN = os.environ.get("PSAM_FUSED_INNER_LN", "1") != "0"  # SwiGLU.norm folded into the fc1 / fc2 GEMM epilogues
 FUSED_MASK_DOT = os.environ.get("PSAM_FUSED_MASK_DOT", "1") != "0"
+# the decoder's projections of the G patch rows (keys of the two-way transformer, 512 rows at c2) on the tcgen05 GEMM instead of
+# the fp32 SIMT linear; the token-side (<= 16 rows) projections stay SIMT
+DECODER_TC = os.environ.get("PSAM_DECODER_TC", "1") != "0"
 # norm1 / norm2 / fc_norm folded into the qkv / fc1 / out_proj GEMMs: the producer of the residual stream (pos_embed, proj and
 # fc2 GEMM epilogues) writes x as fp32 + split-bf16 and accumulates the row statistics, so no LayerNorm kernel runs in a block
 FUSED_BLOCK_LN = os.environ.get("PSAM_FUSED_BLOCK_LN", "1") != "0"
@@ -623,6 +626,17 @@ class _PackedDecoder:
                 act=a, n3=_ln(l.norm3), n4=_ln(l.norm4), i2t=_PackedAttn(l.cross_attn_image_to_token), skip=l.skip_first_layer_pe))
         self.final = _PackedAttn(tr.final_attn_token_to_image)
         self.nf = _ln(tr.norm_final_attn)
+        self.tc = DECODER_TC
+        if self.tc:
+            # patch-row projections as split-bf16 GEMM operands: per layer [k_proj of token->patch ; q_proj of patch->token] act
+            # on (keys + pe), v_proj of token->patch on keys
+            for l in self.layers:
+                t2i, i2t = l["t2i"], l["i2t"]
+                l["wkq"] = ops.pack_weight(torch.cat([t2i.wk, i2t.wq]))
+                l["bkq"] = torch.cat([t2i.bk, i2t.bq]).contiguous()
+                l["wv"] = ops.pack_weight(t2i.wv)
+                l["n_k"] = t2i.wk.shape[0]
+            self.wk_f, self.wv_f = ops.pack_weight(self.final.wk), ops.pack_weight(self.final.wv)
         self.iou_token, self.mask_tokens = _f32(md.iou_token.weight), _f32(md.mask_tokens.weight)
         self.nmt = md.num_mask_tokens
         self.hyper = []
@@ -631,6 +645,8 @@ class _PackedDecoder:
                                torch.stack([_f32(m.layers[li].bias) for m in md.output_hypernetworks_mlps]).contiguous()))
         up = md.output_upscaling
         self.up0w, self.up0b = _f32(up[0].weight), _f32(up[0].bias)
+        if DECODER_TC:
+            self.up0w_s = ops.pack_weight(up[0].weight)
         self.up1 = _ln(up[1])
         self.up3w, self.up3b = ops.pack_weight(up[3].weight), _f32(up[3].bias)
         self.iou = [(_f32(l.weight), _f32(l.bias)) for l in md.iou_prediction_head.layers]
@@ -682,6 +698,8 @@ def run_mask_decoder(md, pc_embeddings, pc_pe, sparse, dense, aux, multimask_out
     pe_z = ops.add_bcast(torch.zeros_like(src), pc_pe.float().contiguous(), chunk=G * D, rep=rep)  # repeat_interleave(pc_pe)
 
     queries, keys, qpe = tokens, src, tokens
+    if pk.tc:
+        return _run_decoder_tc(pk, queries, keys, qpe, pe_z, aux, Z, T, G, D, rep, ids, mask_slice, dev)
     for l in pk.layers:
         if l["skip"]:
             queries = _add_ln(_attend(l["sa"], queries, None, queries, None, queries, Z, T, T), None, l["n1"])
@@ -692,13 +710,63 @@ def run_mask_decoder(md, pc_embeddings, pc_pe, sparse, dense, aux, multimask_out
         queries = _add_ln(queries, ops.linear_f32(h, l["w2"], l["b2"]), l["n3"])
         keys = _add_ln(keys, _attend(l["i2t"], keys, pe_z, queries, qpe, queries, Z, G, T), l["n4"])
     queries = _add_ln(queries, _attend(pk.final, queries, qpe, keys, pe_z, keys, Z, T, G), pk.nf)
-    hs = queries  # [Z*T, D]
+    f0 = ops.linear_f32(keys, pk.up0w, pk.up0b)  # [Z*G, D]
+    return _decoder_heads(pk, queries, f0, aux, Z, T, G, D, rep, ids, mask_slice, dev)
 
+
+def _run_decoder_tc(pk, queries, keys, qpe, pe_z, aux, Z, T, G, D, rep, ids, mask_slice, dev):
+    """Two-way transformer (transformer.py:55-180) with the patch-row projections on tensor cores.  keys_s / keyspe_s are the
+    split-bf16 copies of keys and keys + pe; the LayerNorm that updates keys refreshes both."""
+    ZG = Z * G
+    keys_s, keyspe_s = Split(ZG, D, dev), Split(ZG, D, dev)
+    ops.split_f32(keys, keys_s)
+    ops.split_f32(keys, keyspe_s, add=pe_z)
+    for l in pk.layers:
+        sa, t2i, i2t = l["sa"], l["t2i"], l["i2t"]
+        if l["skip"]:
+            queries = _add_ln(_attend(sa, queries, None, queries, None, queries, Z, T, T), None, l["n1"])
+        else:
+            queries = _add_ln(queries, _attend(sa, queries, qpe, queries, qpe, queries, Z, T, T), l["n1"])
+        nk = l["n_k"]
+        kq = torch.empty((ZG, l["bkq"].shape[0]), dtype=torch.float32, device=dev)  # [:, :nk] = k of t2i, [:, nk:] = q of i2t
+        ops.gemm(keyspe_s, l["wkq"], bias=l["bkq"], out_f32=kq, passes=PASSES)
+        vv = torch.empty((ZG, t2i.wv.shape[0]), dtype=torch.float32, device=dev)
+        ops.gemm(keys_s, l["wv"], bias=t2i.bv, out_f32=vv, passes=PASSES)
+        # tokens -> patches
+        q = ops.linear_f32(queries, t2i.wq, t2i.bq, x2=qpe)
+        o = ops.attention_f32(q, kq, vv, Z, T, G, t2i.H, t2i.inner // t2i.H)
+        queries = _add_ln(queries, ops.linear_f32(o, t2i.wo, t2i.bo), l["n2"])
+        h = ops.linear_f32(queries, l["w1"], l["b1"], act=l["act"])
+        queries = _add_ln(queries, ops.linear_f32(h, l["w2"], l["b2"]), l["n3"])
+        # patches -> tokens
+        k2 = ops.linear_f32(queries, i2t.wk, i2t.bk, x2=qpe)
+        v2 = ops.linear_f32(queries, i2t.wv, i2t.bv)
+        o2 = ops.attention_f32(kq, k2, v2, Z, G, T, i2t.H, i2t.inner // i2t.H, q_off=nk)
+        upd = ops.linear_f32(o2, i2t.wo, i2t.bo)
+        new_keys = torch.empty_like(keys)
+        n4 = l["n4"]
+        ops.layernorm(keys, n4[0], n4[1], n4[2], r=upd, out_f32=new_keys, out_split=keys_s, post_add=pe_z, out_split2=keyspe_s)
+        keys = new_keys
+    kf = torch.empty((ZG, pk.final.wk.shape[0]), dtype=torch.float32, device=dev)
+    ops.gemm(keyspe_s, pk.wk_f, bias=pk.final.bk, out_f32=kf, passes=PASSES)
+    vf = torch.empty((ZG, pk.final.wv.shape[0]), dtype=torch.float32, device=dev)
+    ops.gemm(keys_s, pk.wv_f, bias=pk.final.bv, out_f32=vf, passes=PASSES)
+    q = ops.linear_f32(queries, pk.final.wq, pk.final.bq, x2=qpe)
+    o = ops.attention_f32(q, kf, vf, Z, T, G, pk.final.H, pk.final.inner // pk.final.H)
+    queries = _add_ln(queries, ops.linear_f32(o, pk.final.wo, pk.final.bo), pk.nf)
+    f0 = torch.empty((ZG, D), dtype=torch.float32, device=dev)
+    ops.gemm(keys_s, pk.up0w_s, bias=pk.up0b, out_f32=f0, passes=PASSES)
+    return _decoder_heads(pk, queries, f0, aux, Z, T, G, D, rep, ids, mask_slice, dev)
+
+
+def _decoder_heads(pk, queries, f0, aux, Z, T, G, D, rep, ids, mask_slice, dev):
+    """mask_decoder.py:146-184: upsampling, hyper-network product, IoU head.  f0 = output_upscaling[0](keys) [Z*G, D]."""
+    hs = queries  # [Z*T, D]
+    C = len(ids)
     # upscaling (mask_decoder.py:146-164): Linear0 commutes with the (affine, weights sum to 1) interpolation
     if aux.interp_index is None or aux.interp_weight is None:
         aux.interp_index, aux.interp_weight = ops.knn3_interp(aux.coords.float().contiguous(), aux.centers)
     N = aux.coords.shape[1]
-    f0 = ops.linear_f32(keys, pk.up0w, pk.up0b)  # [Z*G, D]
     u1 = Split(Z * N, D, dev)
     nv.check(nv.lib().psam_interp_ln_gelu(nv.ptr(f0), Z, rep, G, D, nv.ptr(aux.interp_index), nv.ptr(aux.interp_weight), N,
                                           nv.ptr(pk.up1[0]), nv.ptr(pk.up1[1]), pk.up1[2], u1.ptr(), u1.plane, u1.pitch,

@@ -51,7 +51,8 @@ class LnArgs(Structure):
                 ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float),
                 ("rows", c_int), ("D", c_int), ("act", c_int),
                 ("y", c_void_p), ("ldy", c_longlong),
-                ("y_hi", c_void_p), ("y_plane", c_longlong), ("ldy_s", c_longlong), ("pitch", c_longlong), ("padded", c_int), ("policy", c_int)]
+                ("y_hi", c_void_p), ("y_plane", c_longlong), ("ldy_s", c_longlong), ("pitch", c_longlong), ("padded", c_int), ("policy", c_int),
+                ("post_add", c_void_p), ("ld_post", c_longlong), ("y2_hi", c_void_p), ("y2_plane", c_longlong), ("ldy2_s", c_longlong)]
 
 
 EXPORTS = [
@@ -59,7 +60,7 @@ EXPORTS = [
     "psam_border_prompt_workspace_bytes", "psam_border_prompt_f32",
     "psam_gemm_bf16x3", "psam_attention_bf16x3", "psam_attention_bf16x3_twopass", "psam_linear_f32", "psam_layernorm_f32", "psam_swiglu_ln", "psam_small_in_linear",
     "psam_group_max", "psam_softmax_split", "psam_transpose_split", "psam_posenc_f32", "psam_attention_f32",
-    "psam_decoder_prepare", "psam_interp_ln_gelu", "psam_mask_dot", "psam_add_bcast_f32", "psam_split_f32",
+    "psam_decoder_prepare", "psam_interp_ln_gelu", "psam_mask_dot", "psam_add_bcast_f32", "psam_split_f32", "psam_split_add_f32",
     "psam_version",
 ]
 
@@ -102,6 +103,7 @@ def lib():
             "psam_mask_dot": [p, ll, p, i, i, i, i, p, p],
             "psam_add_bcast_f32": [p, p, ll, ll, ll, ll, p, p],
             "psam_split_f32": [p, ll, ll, i, p, ll, ll, ll, p],
+            "psam_split_add_f32": [p, p, ll, ll, i, p, ll, ll, ll, p],
         }
         for name, args in sig.items():
             fn = getattr(L, name)

@@ -199,7 +199,8 @@ def linear_f32(x, w, b=None, *, x2=None, r=None, act=ACT_NONE, out=None, M=None,
 
 
 def layernorm(x, gamma, beta, eps, *, rows=None, D=None, r=None, gbias=None, group_rows=0, act=ACT_NONE,
-              out_f32: Optional[torch.Tensor] = None, out_split: Optional[Split] = None, ldx=None, padded: bool = False):
+              out_f32: Optional[torch.Tensor] = None, out_split: Optional[Split] = None, ldx=None, padded: bool = False,
+              post_add: Optional[torch.Tensor] = None, out_split2: Optional[Split] = None):
     D = D if D is not None else x.shape[-1]
     rows = rows if rows is not None else x.numel() // x.shape[-1]
     a = LnArgs()
@@ -212,6 +213,9 @@ def layernorm(x, gamma, beta, eps, *, rows=None, D=None, r=None, gbias=None, gro
     if out_split is not None:
         a.y_hi, a.y_plane, a.ldy_s, a.pitch = out_split.ptr(), out_split.plane, out_split.pitch, out_split.pitch
     a.padded = int(padded)
+    if out_split2 is not None:  # second split output = split(y + post_add)
+        a.post_add, a.ld_post = nv.ptr(post_add), post_add.shape[-1]
+        a.y2_hi, a.y2_plane, a.ldy2_s = out_split2.ptr(), out_split2.plane, out_split2.pitch
     a.policy = GEMM_TILE_HINT  # same switch as the GEMM tile policy: 1 while capturing the pipelined predictor's graphs
     nv.check(nv.lib().psam_layernorm_f32(byref(a), nv.stream()), "layernorm")
 
@@ -252,10 +256,11 @@ def posenc(coords, gauss, labels=None, emb0=None, emb1=None, bad_flag=None):
     return out
 
 
-def attention_f32(q, k, v, Z, Lq, Lk, H, dh):
+def attention_f32(q, k, v, Z, Lq, Lk, H, dh, q_off=0, k_off=0, v_off=0):
+    """q / k / v may be column windows of wider row-major tensors: *_off = first column, the row stride is the tensor's width."""
     o = torch.empty((Z * Lq, H * dh), dtype=torch.float32, device=q.device)
-    nv.check(nv.lib().psam_attention_f32(nv.ptr(q), nv.ptr(k), nv.ptr(v), nv.ptr(o), Z, Lq, Lk, H, dh, q.shape[-1], k.shape[-1],
-                                         v.shape[-1], H * dh, nv.stream()), "attention_f32")
+    nv.check(nv.lib().psam_attention_f32(nv.ptr(q) + 4 * q_off, nv.ptr(k) + 4 * k_off, nv.ptr(v) + 4 * v_off, nv.ptr(o), Z, Lq, Lk, H,
+                                         dh, q.shape[-1], k.shape[-1], v.shape[-1], H * dh, nv.stream()), "attention_f32")
     return o
 
 
@@ -267,7 +272,12 @@ def add_bcast(a, b, chunk=None, rep=1):
     return out
 
 
-def split_f32(x: torch.Tensor, out: Split):
+def split_f32(x: torch.Tensor, out: Split, add: Optional[torch.Tensor] = None):
+    """out = split-bf16(x (+ add))."""
     rows = x.numel() // x.shape[-1]
-    nv.check(nv.lib().psam_split_f32(nv.ptr(x), x.shape[-1], rows, x.shape[-1], out.ptr(), out.plane, out.pitch, out.pitch,
-                                     nv.stream()), "split_f32")
+    if add is None:
+        nv.check(nv.lib().psam_split_f32(nv.ptr(x), x.shape[-1], rows, x.shape[-1], out.ptr(), out.plane, out.pitch, out.pitch,
+                                         nv.stream()), "split_f32")
+    else:
+        nv.check(nv.lib().psam_split_add_f32(nv.ptr(x), nv.ptr(add), x.shape[-1], rows, x.shape[-1], out.ptr(), out.plane, out.pitch,
+                                             out.pitch, nv.stream()), "split_add_f32")

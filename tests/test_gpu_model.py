@@ -65,6 +65,31 @@ def test_golden_end_to_end(golden_dir, name, fold_ln, fold_block, monkeypatch):
     np.testing.assert_allclose(masks.cpu().numpy(), g["masks_mm"], atol=ATOL, rtol=RTOL)
 
 
+@pytest.mark.parametrize("tc", [True, False])
+def test_decoder_patch_row_projections_tensor_core_and_simt(tc, monkeypatch):
+    """The two-way transformer's projections of the G patch rows run on the tcgen05 GEMM (keys / keys + pe kept as
+    split-bf16 by the LayerNorm that updates them) or on the fp32 SIMT linear: both against the oracle, 2 prompts per
+    cloud x 2 masks per cloud (Z = B*M = 4) and a prompt-mask pass."""
+    from psam_b200 import engine
+
+    monkeypatch.setattr(engine, "DECODER_TC", tc)
+    model, oracle = _build("eva02_test_tiny", 96, 16, 3)
+    xyz, feats = synth.make_batch(2, 3000, 8)
+    pc = synth.make_prompts(xyz, 4, 8)[0].reshape(4, 2, 3)
+    pl = synth.make_prompts(xyz, 4, 8)[1].reshape(4, 2)
+    d = torch.device("cuda:0")
+    with torch.no_grad():
+        want_m, want_i = oracle.predict_masks(xyz, feats, pc, pl, None, True)
+        got_m, got_i = model.predict_masks(xyz.to(d), feats.to(d), pc.to(d), pl.to(d), None, True)
+        pm = want_m[:, 1]
+        want2, _ = oracle.predict_masks(xyz, feats, pc, pl, pm, False)
+        got2, _ = model.predict_masks(xyz.to(d), feats.to(d), pc.to(d), pl.to(d), pm.to(d), False)
+    _report(f"decoder tc={tc}", got_m.cpu(), want_m)
+    np.testing.assert_allclose(got_m.cpu().numpy(), want_m.numpy(), atol=ATOL, rtol=RTOL)
+    np.testing.assert_allclose(got_i.cpu().numpy(), want_i.numpy(), atol=ATOL, rtol=RTOL)
+    np.testing.assert_allclose(got2.cpu().numpy(), want2.numpy(), atol=ATOL, rtol=RTOL)
+
+
 def test_golden_tie_heavy_tokenizer(golden_dir):
     """Quantised grid with duplicated points: FPS must follow the reference tie-break bit for bit."""
     g = np.load(os.path.join(golden_dir, "tiny_ties.npz"))

@@ -7,7 +7,7 @@ echo "== attention tests"; timeout 500 python -m pytest tests/test_gpu_kernels.p
 echo "== kernel tests"; timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --deselect tests/test_gpu_kernels.py::test_fused_attention_tc 2>&1 | tail -25 | tee $O/r2_kernels.log
 echo "== model tests"; timeout 1500 python -m pytest tests/test_gpu_model.py -m gpu -q -s 2>&1 | grep -E "parity|passed|failed|Error|error|assert" | tail -60 | tee $O/r2_model.log
 echo "== bench A/B"
-for cfg in "new::" "noblockln:PSAM_FUSED_BLOCK_LN=0:" "nodual:PSAM_GEMM_VARIANT=0x10:" "nodual_noblockln:PSAM_FUSED_BLOCK_LN=0 PSAM_GEMM_VARIANT=0x10:" "twopass:PSAM_ATTENTION_TWOPASS=1:" "r1like:PSAM_FUSED_BLOCK_LN=0 PSAM_GEMM_VARIANT=0x10 PSAM_ATTENTION_TWOPASS=1:"; do
+for cfg in "new::" "noblockln:PSAM_FUSED_BLOCK_LN=0:" "nodual:PSAM_GEMM_VARIANT=0x10:" "nodual_noblockln:PSAM_FUSED_BLOCK_LN=0 PSAM_GEMM_VARIANT=0x10:" "twopass:PSAM_ATTENTION_TWOPASS=1:" "nodectc:PSAM_DECODER_TC=0:" "r1like:PSAM_FUSED_BLOCK_LN=0 PSAM_GEMM_VARIANT=0x10 PSAM_ATTENTION_TWOPASS=1 PSAM_DECODER_TC=0:"; do
   name=${cfg%%:*}; rest=${cfg#*:}; envs=${rest%%:*}
   env $envs timeout 400 $B > $O/r2_ab_$name.json 2> $O/r2_ab_$name.err
   python - <<PY
