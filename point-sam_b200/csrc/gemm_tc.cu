@@ -35,7 +35,7 @@ constexpr int GEMM_EPI_PER_QUARTER = 4;                         // default: 16 e
 constexpr int gemm_threads(int epq) { return 64 + 128 * epq; }  // TMA warp, MMA warp, 4*epq epilogue warps
 constexpr int GEMM_THREADS = gemm_threads(GEMM_EPI_PER_QUARTER);
 // psam_gemm_out.variant bits (experiment / policy switches; no environment variable is read inside the library)
-constexpr int GV_2CTA = 0x1, GV_BK32 = 0x2, GV_SCALAR_EPI = 0x4, GV_DUAL = 0x8, GV_NO_DUAL = 0x10;
+constexpr int GV_2CTA = 0x1, GV_BK32 = 0x2, GV_SCALAR_EPI = 0x4, GV_DUAL = 0x8, GV_NO_DUAL = 0x10, GV_PERSIST = 0x20, GV_NO_PERSIST = 0x40;
 
 struct GemmEpilogue {
     float* out_f32;            // may be null
@@ -326,14 +326,15 @@ __device__ __forceinline__ void epi_chunk_v4_dispatch(float* stg, const uint32_t
 __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const GemmEpilogue& ep, unsigned char* smem_aligned,
                                               uint32_t tmem_base, uint32_t tmem_full_bar_addr, int warp, int lane, int m_tile,
                                               int n_tile, int b1, int b2, int split, int num_kb, int BN,
-                                              int epq = GEMM_EPI_PER_QUARTER) {
+                                              int epq = GEMM_EPI_PER_QUARTER, uint32_t full_parity = 0u) {
         const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
         const int row0 = m_tile * GEMM_BM + quarter * 32;
         if (num_kb > 0) {
-            mbar_wait(tmem_full_bar_addr, 0);
+            mbar_wait(tmem_full_bar_addr, full_parity);
             tc_fence_after();
         }
-        // All TMA loads have landed and all MMAs have retired: the pipeline stages are free to reuse.
+        // One-shot kernels: all TMA loads have landed and all MMAs have retired, the pipeline stages are free to reuse
+        // (smem_aligned = stage memory).  Persistent kernel: smem_aligned points at a dedicated staging area.
         float* stg = reinterpret_cast<float*>(smem_aligned) + (warp - 2) * (32 * EPI_PITCH);  // 16-byte aligned rows
         const int ehalf = (warp - 2) >> 2;  // the warps of a lane quarter take interleaved 32-column chunks
         const long long obase = (long long)b1 * ep.out_b1 + (long long)b2 * ep.out_b2;
@@ -586,6 +587,157 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
 
 // ---------------------------------------------------------------------------------------------
+// Persistent variant: grid = min(tiles, SMs); every CTA walks the linear tile index (m fastest, so the CTAs running at the
+// same time share W tiles through L2) with a stride of gridDim.x.  The accumulator is DOUBLE-BUFFERED in tensor memory
+// (2 x ACC_COLS columns): the epilogue warps drain tile i while the MMA warp already accumulates tile i+1, and the TMA
+// producer never stops - the shared-memory stage ring runs across tile boundaries.  The one-shot kernel above pays
+// TMEM allocation, barrier setup, pipeline fill and the whole epilogue once per 128 x BN tile with the tensor pipe idle;
+// here they are paid once per CTA, or hidden.  The epilogue has its own staging memory (the stage ring is never idle), so
+// the wide-tile configuration uses BK = 32 stages (48 KB) x 4 with four epilogue warps.
+// ---------------------------------------------------------------------------------------------
+template <int MAXBN, int STAGES, int BK, int EPQ>
+__global__ void __launch_bounds__(gemm_threads(EPQ), 1)
+gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmShape shape,
+                       const GemmEpilogue ep) {
+    pdl_launch_dependents();
+    using S = GemmSmem<MAXBN, STAGES, BK>;
+    constexpr int ACC_COLS = S::TMEM_COLS;
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
+    unsigned char* staging = smem_aligned + STAGES * S::STAGE;  // 4*EPQ warps x 32 x EPI_PITCH floats
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int BN = shape.bn;
+    const int MT = ceil_div(shape.M, GEMM_BM), NT = ceil_div(shape.N, BN);
+    const int total = MT * NT * shape.nb1 * shape.nb2 * shape.split_k;
+    const int kb_total = (shape.K + BK - 1) / BK;
+    const int kb_per = (kb_total + shape.split_k - 1) / shape.split_k;
+    const bool lo_pass = shape.passes == 3;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&acc_full[b]), 1);
+            mbar_init(smem_u32(&acc_empty[b]), 4 * EPQ);  // one arrival per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 2 * ACC_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();
+
+    // tile -> (m_tile, n_tile, b1, b2, split) and its k-block range; identical in the three roles
+    auto decode = [&](int tile, int& m_tile, int& n_tile, int& b1, int& b2, int& split, int& kb_begin, int& num_kb) {
+        m_tile = tile % MT;
+        n_tile = (tile / MT) % NT;
+        const int z = tile / (MT * NT);
+        split = z % shape.split_k;
+        const int bz = z / shape.split_k;
+        b1 = bz % shape.nb1, b2 = bz / shape.nb1;
+        kb_begin = split * kb_per;
+        num_kb = max(0, min(kb_total, kb_begin + kb_per) - kb_begin);
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer: lane 0 streams A, lane 1 streams W =====================
+        if (lane < 2) {
+            const uint32_t stage_bytes = (lo_pass ? 2u : 1u) * (uint32_t)(S::A_TILE + BN * BK * 2);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                int m_tile, n_tile, b1, b2, split, kb_begin, num_kb;
+                decode(tile, m_tile, n_tile, b1, b2, split, kb_begin, num_kb);
+                for (int i = 0; i < num_kb; ++i, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                    const uint32_t fb = smem_u32(&full_bar[s]);
+                    const uint32_t sa = smem_base + s * S::STAGE;
+                    const int k0 = (kb_begin + i) * BK;
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(fb, stage_bytes);
+                        tma_load_5d(sa, &tmap_a, fb, k0, m_tile * GEMM_BM, 0, b1, b2);
+                    } else {
+                        tma_load_5d(sa + 2 * S::A_TILE, &tmap_b, fb, k0, n_tile * BN, 0, b1, b2);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+        uint32_t it = 0, acc_it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            int m_tile, n_tile, b1, b2, split, kb_begin, num_kb;
+            decode(tile, m_tile, n_tile, b1, b2, split, kb_begin, num_kb);
+            if (num_kb == 0) continue;
+            const uint32_t ab = acc_it & 1u;
+            mbar_wait(smem_u32(&acc_empty[ab]), ((acc_it >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_acc = tmem_base + ab * (uint32_t)ACC_COLS;
+            for (int i = 0; i < num_kb; ++i, ++it) {
+                const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_base + s * S::STAGE;
+                    const uint64_t a_hi = umma_desc_k<BK>(sa);
+                    const uint64_t a_lo = umma_desc_k<BK>(sa + S::A_TILE);
+                    const uint64_t b_hi = umma_desc_k<BK>(sa + 2 * S::A_TILE);
+                    const uint64_t b_lo = umma_desc_k<BK>(sa + 2 * S::A_TILE + BN * BK * 2);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_bf16(d_acc, a_hi + 2 * k, b_hi + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    if (lo_pass) {
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) umma_bf16(d_acc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) umma_bf16(d_acc, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                    }
+                    umma_commit(smem_u32(&empty_bar[s]));
+                    if (i == num_kb - 1) umma_commit(smem_u32(&acc_full[ab]));
+                }
+                __syncwarp();
+            }
+            ++acc_it;
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        uint32_t acc_it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            int m_tile, n_tile, b1, b2, split, kb_begin, num_kb;
+            decode(tile, m_tile, n_tile, b1, b2, split, kb_begin, num_kb);
+            const uint32_t ab = acc_it & 1u;
+            gemm_epilogue(shape, ep, staging, tmem_base + ab * (uint32_t)ACC_COLS, smem_u32(&acc_full[ab]), warp, lane, m_tile, n_tile,
+                          b1, b2, split, num_kb, BN, EPQ, (acc_it >> 1) & 1u);
+            if (num_kb > 0) {
+                tc_fence_before();  // this warp's tcgen05.ld of the accumulator are complete
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&acc_empty[ab]));
+                ++acc_it;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * ACC_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 2-CTA variant (tcgen05 cta_group::2): two CTAs of a cluster (consecutive m-tiles) act as one 256 x BN MMA.
 // Each CTA streams its own 128 A rows and only HALF of the W tile (BN/2 rows); the tensor cores of the pair read
 // both halves, so the operand bytes ingested per SM and flop drop by 1/3 (BN=256: 64 KB instead of 96 KB per
@@ -814,6 +966,19 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
     return PSAM_OK;
 }
 
+template <int MAXBN, int STAGES, int BK, int EPQ>
+static int launch_gemm_persist(const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& sh, const GemmEpilogue& ep,
+                               int ctas, cudaStream_t stream) {
+    auto kern = gemm_tc_persist_kernel<MAXBN, STAGES, BK, EPQ>;
+    using S = GemmSmem<MAXBN, STAGES, BK>;
+    constexpr int SMEM = STAGES * S::STAGE + 4 * EPQ * 32 * EPI_PITCH * 4 + 1024;
+    static_assert(SMEM <= 232448, "shared memory budget of one SM");
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    PSAM_CUDA_TRY(psam::launch(kern, dim3((unsigned)ctas), dim3(gemm_threads(EPQ)), (size_t)SMEM, stream, ma, mb, sh, ep));
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
 template <int MAXBN, int STAGES>
 static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mbh, const GemmShape& sh, const GemmEpilogue& ep,
                         cudaStream_t stream) {
@@ -960,6 +1125,30 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     if (rc) return rc;
     rc = make_operand_map(&mbmc, w, bn / cm, 1);
     if (rc) return rc;
+    // Persistent kernel (double-buffered TMEM accumulator, stage ring running across tiles): whenever a CTA would get at
+    // least two tiles (many-row GEMMs: the mini-PointNet, batched clouds), or on request (GV_PERSIST; bits 16-19 = tiles per
+    // CTA to aim for, which trades SMs occupied by this launch against its length).
+    {
+        int nsm = 148, devid = 0;
+        if (cudaGetDevice(&devid) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, devid);
+        const long long total = (long long)ceil_div(sh.N, bn) * mtiles * sh.nb1 * sh.nb2 * sh.split_k;
+        const int want = (variant >> 16) & 15;
+        const bool persist = cm == 1 && !(variant & GV_NO_PERSIST) && total < (1ll << 30) &&
+                             ((variant & GV_PERSIST) || total >= 2ll * nsm);
+        if (persist) {
+            long long per = ceil_div_ll(total, nsm);       // tiles per CTA when the launch spreads over all SMs
+            if (want > per) per = want;
+            const int ctas = (int)ceil_div_ll(total, per);  // balanced: every CTA gets `per` (or per - 1) tiles
+            const int bkp = bn > 128 ? 32 : 64;
+            rc = make_operand_map(&ma, a, GEMM_BM, passes == 3 ? 2 : 1, bkp);
+            if (rc) return rc;
+            rc = make_operand_map(&mb, w, bn, passes == 3 ? 2 : 1, bkp);
+            if (rc) return rc;
+            if (bn > 128) return launch_gemm_persist<256, 4, 32, 1>(ma, mb, sh, ep, ctas, stream);
+            if (bn > 64) return launch_gemm_persist<128, 3, 64, 1>(ma, mb, sh, ep, ctas, stream);
+            return launch_gemm_persist<64, 4, 64, 1>(ma, mb, sh, ep, ctas, stream);
+        }
+    }
     // wide tiles, throughput policy: the dual-resident configuration (two 97 KB CTAs per SM, BK = 32, 2 stages each);
     // GV_DUAL forces it for any wide tile, GV_NO_DUAL keeps the one-CTA-per-SM kernel.
     // GV_BK32: one CTA per SM with 4 half-size stages.  MEASURED round 1: 611 vs 618 clouds/s - no gain, opt-in.

@@ -291,7 +291,10 @@ class _PackedBlock:
             bias = lambda lin: lin.bias.detach().float() if lin.bias is not None else zeros
             bqkv = torch.cat([bias(at.q_proj), bias(at.k_proj), bias(at.v_proj)])
         self.wqkv, self.bqkv = ops.pack_weight(wqkv), bqkv.contiguous()
-        self.fold_block = FUSED_BLOCK_LN
+        # the folded forms live in the GEMM's vectorised epilogue (whole 32-column chunks): D and the MLP width must be
+        # multiples of 32, otherwise the block keeps its LayerNorm kernels
+        mlp_w = blk.mlp.fc1_g.out_features if hasattr(blk.mlp, "fc1_g") else blk.mlp.fc1.out_features
+        self.fold_block = FUSED_BLOCK_LN and D % 32 == 0 and (hasattr(blk.mlp, "fc1_g") or mlp_w % 32 == 0)
         if self.fold_block:
             # LN(x) @ W^T + b = rstd * (x @ (W gamma)^T - mean * (W gamma) 1) + (W beta + b)
             self.wqkv_f, self.cqkv, self.bqkv_f = _fold_ln(wqkv, bqkv, blk.norm1)
@@ -344,7 +347,10 @@ class _PackedEncoder:
         self.tail = [(_f32(m.weight), _f32(m.bias), m.eps) for m in validate_transformer(enc.transformer)]
         self.blocks = [_PackedBlock(b, D) for b in enc.transformer.blocks]
         self.wout, self.bout = ops.pack_weight(enc.out_proj.weight), _f32(enc.out_proj.bias)
-        self.fold_block = FUSED_BLOCK_LN and len(self.tail) == 1 and all(b.fold_block for b in self.blocks)
+        self.fold_block = (FUSED_BLOCK_LN and len(self.tail) == 1 and all(b.fold_block for b in self.blocks)
+                           and enc.embed_dim % 32 == 0)
+        for b in self.blocks:
+            b.fold_block = self.fold_block
         if self.fold_block:
             m = validate_transformer(enc.transformer)[0]
             self.wout_f, self.cout, self.bout_f = _fold_ln(enc.out_proj.weight.detach().float(), enc.out_proj.bias.detach().float(), m)

@@ -559,7 +559,9 @@ def test_fused_attention_tc_reference_maximum_moves(L):
     assert float((got - got2).abs().max()) < 5e-5 * max(1.0, float(want.abs().max()))
 
 
-@pytest.mark.parametrize("variant", ["bn256_bk32", "bn256_bk64", "two_cta", "cluster4", "dual_resident", "throughput_policy"])
+@pytest.mark.parametrize("variant", ["bn256_bk32", "bn256_bk64", "two_cta", "cluster4", "dual_resident", "throughput_policy",
+                                     "persistent_bn256", "persistent_bn128", "persistent_bn64", "persistent_3_tiles_per_cta",
+                                     "never_persistent"])
 def test_gemm_tc_variants(variant, monkeypatch):
     """Opt-in / policy-selected GEMM variants (psam_gemm_out.variant / tile_hint; the library reads no environment):
     wide tiles with 64-byte-swizzled half-depth stages, the same with 128-byte swizzle, the 2-CTA cta_group::2 kernel,
@@ -567,7 +569,12 @@ def test_gemm_tc_variants(variant, monkeypatch):
     throughput policy (tile_hint = 1, as baked into the pipelined predictor's graphs) selects."""
     ops = _ops()
     bn, var, hint = {"bn256_bk32": (256, ops.GV_BK32, 0), "bn256_bk64": (256, ops.GV_NO_DUAL, 0), "two_cta": (0, ops.GV_2CTA, 0),
-                     "cluster4": (128, 4 << 8, 0), "dual_resident": (256, ops.GV_DUAL, 0), "throughput_policy": (0, 0, 1)}[variant]
+                     "cluster4": (128, 4 << 8, 0), "dual_resident": (256, ops.GV_DUAL, 0), "throughput_policy": (0, 0, 1),
+                     # persistent kernel (double-buffered TMEM accumulator, tile loop inside the CTA) at its three tile widths,
+                     # with several tiles per CTA forced, and switched off (the one-shot kernels on the many-row shape)
+                     "persistent_bn256": (256, ops.GV_PERSIST, 0), "persistent_bn128": (128, ops.GV_PERSIST, 0),
+                     "persistent_bn64": (64, ops.GV_PERSIST, 0), "persistent_3_tiles_per_cta": (0, ops.GV_PERSIST | (3 << 16), 1),
+                     "never_persistent": (0, ops.GV_NO_PERSIST, 1)}[variant]
     monkeypatch.setattr(ops, "GEMM_TILE_BN", bn)
     monkeypatch.setattr(ops, "GEMM_VARIANT", var)
     monkeypatch.setattr(ops, "GEMM_TILE_HINT", hint)

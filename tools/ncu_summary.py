@@ -1,5 +1,5 @@
 """ncu report -> short markdown table of the metrics the profiles/ summaries quote.
-usage: python tools/ncu_summary.py file.ncu-rep out.md "free text header" [kernel-name-substring]"""
+usage: python tools/ncu_summary.py file.ncu-rep|raw.csv out.md "free text header" [kernel-name-substring]"""
 import csv
 import io
 import subprocess
@@ -14,7 +14,9 @@ KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_xu.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
         "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct"]
-raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# a .csv argument is the `--page raw --csv` export made on the GPU box (the .ncu-rep itself can exceed the gpurun_out/ cap)
+raw = open(sys.argv[1]).read() if sys.argv[1].endswith(".csv") else \
+    subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 head, units = rows[0], rows[1]
 want = sys.argv[4] if len(sys.argv) > 4 else None
