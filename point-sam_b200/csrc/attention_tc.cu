@@ -53,7 +53,18 @@ struct AttnParams {
     float scale_log2e;  // softmax scale * log2(e)
     __nv_bfloat16* out_hi;
     long long out_plane, ldo, out_h, out_b;  // elements: plane offset, row stride, head / cloud strides
+    unsigned long long* trace;               // debug timeline (tools/attention_trace.py): null in production
+    int tiles_per_cta;                       // attention_pair_kernel: 1 or 2 query tiles per CTA
 };
+
+__device__ __forceinline__ void att_trace(const AttnParams& p, int slot) {
+    // one 64-bit clock stamp per (CTA, slot); only CTA (0,0,0) records, one lane per call site
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+        p.trace[slot] = t;
+    }
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -551,29 +562,33 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gri
 
 
 // ---------------------------------------------------------------------------------------------------------
-// attention_flow_kernel: the production path for dh = 64 at ANY sequence length.
+// attention_pair_kernel: the production path for dh = 64 at ANY sequence length.
 //
-// The two kernels above run the softmax as two exact sweeps (row maximum first), which serialises the tensor pipe
-// behind the softmax warps (23 % tensor-pipe activity at L = 512, profiles/r01_attention_tc_kernel_ncu_full.md) or
-// recomputes Q K^T (long rows).  This kernel streams the key blocks ONCE:
-//   * S_j = Q K_j^T (split-bf16, 3 passes) lands in one of three 128-column TMEM slots; the MMA warp runs up to
-//     three blocks ahead of the softmax warps (S_0 S_1 S_2 | PV_0 S_3 | PV_1 S_4 | ...).
-//   * softmax warps (2 threads per query row, 64 keys each): S_j -> registers, block maximum (FMNMX3), one named-
-//     barrier exchange between the two threads of a row, P_j = exp2(S_j c - m_ref) with packed fp32x2 arithmetic
-//     (FFMA2 / FADD2), split into bf16 hi / lo and written BACK INTO THE SAME TMEM SLOT (hi in columns [0,64), lo in
-//     [64,128) of the slot, two keys per 32-bit column).  O += P_j V_j then takes P as the TMEM A operand of
-//     tcgen05.mma (V^T is the MN-major smem B operand as before): no shared-memory round trip for P, no proxy fence,
-//     and the freed 64 KB of shared memory hold a 5-deep K/V stage ring.
-//   * the running reference maximum m_ref is only moved when a block maximum exceeds it by more than 2^ATT_TAU
-//     (softmax is shift invariant, P <= 2^ATT_TAU keeps full fp32 / split-bf16 relative precision).  When it moves,
-//     the warps of the affected rows rescale O in TMEM (tcgen05.ld -> mul -> tcgen05.st) after PV_{j-1} has retired -
-//     a rare slow path (never taken when the first block already holds a near-maximal logit).
+// What bounds fused attention on this part (profiles/r02_attention_*): tensor memory is READ at only ~64 B/clk per SM, so
+// fetching a 128 x 128 fp32 S block costs as much (1024 clk) as exponentiating it on the MUFU pipe (1024 clk) and more than
+// the MMAs that produced it (768 clk, three split-bf16 passes); a kernel that fetches, then exponentiates, then stores with
+// one query tile per CTA leaves the tensor pipe idle for two thirds of the CTA's life (31 % active, round-2 streaming
+// kernel; 23 % round-1 two-pass kernel).  This kernel keeps every unit busy at once:
+//   * ONE CTA = TWO query tiles (256 queries) of one (cloud, head): K_j / V_j are loaded once for both tiles and the MMA
+//     warp alternates between them - items g = 2 j + t: S_g = Q_t K_j^T into TMEM slot g % 3, O_t += P_g V_j.  While softmax
+//     group t works on item g, the tensor pipe computes S_{g+1..g+2} and PV_{g-1} of the OTHER tile.
+//   * softmax group t = 4 warps, ONE THREAD PER QUERY ROW (all 128 keys of the block): no cross-thread exchange, no named
+//     barrier.  The row is processed in four 32-key chunks; tcgen05.ld of chunk k+1 is in flight while chunk k is
+//     exponentiated (FFMA2 / MUFU.EX2 / packed cvt) and written BACK IN PLACE as split-bf16 (hi in columns [32k, 32k+16),
+//     lo in [32k+16, 32k+32) of the slot, two keys per 32-bit column).  O_t += P_g V_j takes P as the TMEM A operand of
+//     tcgen05.mma and V^T as an MN-major shared-memory B operand (no transpose, no shared-memory round trip for P).
+//   * single pass with a LAZY reference maximum: P = exp2(S c - m_ref c).  softmax is shift invariant and every operand is
+//     floating point, so m_ref only has to keep P inside the exponent range: it is moved when a chunk maximum exceeds it by
+//     more than 2^AP_TAU (always at the first chunk of a row, practically never afterwards); the owning thread then rescales
+//     its row of O_t (tcgen05.ld -> mul -> tcgen05.st, after PV of the previous block has retired), its running sum and
+//     the chunks of the current block it has already written.
 // Exactness: the result equals softmax(QK^T c) V up to fp32 rounding (same split-bf16 operands as the other kernels).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int AF_STAGES = 5;
-constexpr int AF_SLOTS = 3;
-constexpr float AF_TAU = 8.0f;  // log2 units
-constexpr int AF_SMEM_TOTAL = ATT_SMEM_Q + AF_STAGES * ATT_SMEM_STAGE + 2 * 2 * 128 * 4 /*row exchange, double buffered*/ + 1024;
+constexpr int AP_STAGES = 4;        // K / V blocks in flight (32 KB each)
+constexpr int AP_SLOTS = 2;         // S / P slots of 128 TMEM columns (with two query tiles: one per softmax group)
+constexpr float AP_TAU = 40.0f;     // log2 units
+constexpr int AP_THREADS = 352;     // warps 0-3: softmax group 0, 4-7: group 1, 8: TMA, 9: S issuer (+ TMEM allocation), 10: PV issuer
+constexpr int AP_SMEM_TOTAL = 2 * ATT_SMEM_Q + AP_STAGES * ATT_SMEM_STAGE + 1024;
 
 // D[tmem] (+)= A[tmem] * B[smem desc]: P is read from tensor memory (row = lane, two bf16 per 32-bit column along K)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -639,86 +654,91 @@ __device__ __forceinline__ float ex2f(float x) {
     return e;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attention_flow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+__device__ __forceinline__ float bf16lo_f(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16hi_f(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+
+__global__ void __launch_bounds__(AP_THREADS, 1)
+attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                       const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
     pdl_launch_dependents();
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t q_full, pv_done;
-    __shared__ __align__(8) uint64_t kv_full[AF_STAGES], kv_empty[AF_STAGES];
-    __shared__ __align__(8) uint64_t s_full[AF_SLOTS], p_full[AF_SLOTS];
+    __shared__ __align__(8) uint64_t q_full, pv_done[2];
+    __shared__ __align__(8) uint64_t kv_full[AP_STAGES], kv_empty[AP_STAGES];
+    __shared__ __align__(8) uint64_t s_full[AP_SLOTS], p_full[AP_SLOTS];
     __shared__ uint32_t tmem_base_smem;
 
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-    const uint32_t sQ = smem_base;
-    const uint32_t sKV = sQ + ATT_SMEM_Q;
+    const uint32_t sQ = smem_base;                    // Q tile t at sQ + t * ATT_SMEM_Q (hi plane, lo plane)
+    const uint32_t sKV = sQ + 2 * ATT_SMEM_Q;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const int q_tile0 = blockIdx.x * p.tiles_per_cta;                          // first of the (up to) two query tiles
+    const int nt = min(p.tiles_per_cta, (p.L + ATT_BQ - 1) / ATT_BQ - q_tile0);  // query tiles of this CTA
     const int nkb = (p.L + ATT_BKEY - 1) / ATT_BKEY;
+    const int G = nt * nkb;                                                    // items: g = j * nt + t
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 8 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_k);
         tma_prefetch_desc(&tmap_v);
         mbar_init(smem_u32(&q_full), 1);
-        mbar_init(smem_u32(&pv_done), 1);
-        for (int s = 0; s < AF_STAGES; ++s) {
+        mbar_init(smem_u32(&pv_done[0]), 1);
+        mbar_init(smem_u32(&pv_done[1]), 1);
+        for (int s = 0; s < AP_STAGES; ++s) {
             mbar_init(smem_u32(&kv_full[s]), 1);
             mbar_init(smem_u32(&kv_empty[s]), 1);
         }
-        for (int s = 0; s < AF_SLOTS; ++s) {
+        for (int s = 0; s < AP_SLOTS; ++s) {
             mbar_init(smem_u32(&s_full[s]), 1);
-            mbar_init(smem_u32(&p_full[s]), 256);
+            mbar_init(smem_u32(&p_full[s]), 128);  // the 128 threads of one softmax group
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+    if (warp == 9) tmem_alloc(smem_u32(&tmem_base_smem), 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
-    const uint32_t t_o = tmem_base;          // O: columns [0, 64)
-    const uint32_t t_s = tmem_base + 64u;    // slot s: columns [64 + 128 s, 64 + 128 s + 128)
+    const uint32_t t_o = tmem_base;           // O_t: columns [128 t, 128 t + 128): P V_hi in the first 64, P V_lo in the last 64
+    const uint32_t t_s = tmem_base + 256u;    // slot s: columns [256 + 128 s, +128)
     pdl_wait();
+    if (threadIdx.x == 0) att_trace(p, 0);  // trace layout: 0 start | 1 q_full seen | 2 + 8 g + {0 S issued, 1 PV issued, 2 s_full seen, 3 first chunk fetched, 4 exps done, 5 p_full arrive} | 200 end
 
-    // Operand blocks travel through the stage ring in the order the MMA warp consumes them:
-    //   K_0 K_1 K_2 | V_0 K_3 | V_1 K_4 | ... | V_{nkb-1}
-    if (warp == 0) {
+    // One thread issues a tcgen05.mma every ~120 clk at best, whatever its size (tools/mma_issue_probe.cu: 122 clk for
+    // N = 64 and N = 128 from one thread, half that from two), and an item needs 12 + 16 of them: a single issuing warp was
+    // the bottleneck of this kernel (softmax warps idle half of the time, profiles/r02).  So TWO warps issue: warp 9 the
+    // S_g = Q_t K_j^T products, warp 10 the O_t += P_g [V_hi | V_lo] products.  The only ordering between them - S_{g+2}
+    // overwrites the slot PV_g reads P from - goes through pv_done (tcgen05.commit of PV_g).
+    // The stage ring carries K_0 V_0 K_1 V_1 ...: K_j at position 2 j (S issuer), V_j at 2 j + 1 (PV issuer); a block is
+    // released after its last use (tile nt - 1).
+    if (warp == 8) {
         if (lane == 0) {
             const uint32_t qb = smem_u32(&q_full);
-            mbar_arrive_expect_tx(qb, ATT_SMEM_Q);
-            tma_load_5d(sQ, &tmap_q, qb, 0, q_tile * ATT_BQ, 0, h, b);
-            int i = 0;
-            auto load = [&](const CUtensorMap* tm, int blk) {
-                const int s = i % AF_STAGES;
-                mbar_wait(smem_u32(&kv_empty[s]), ((uint32_t)(i / AF_STAGES) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(qb, (uint32_t)(nt * ATT_SMEM_Q));
+            for (int t = 0; t < nt; ++t) tma_load_5d(sQ + t * ATT_SMEM_Q, &tmap_q, qb, 0, (q_tile0 + t) * ATT_BQ, 0, h, b);
+            for (int i = 0; i < 2 * nkb; ++i) {
+                const int s = i % AP_STAGES;
+                mbar_wait(smem_u32(&kv_empty[s]), ((uint32_t)(i / AP_STAGES) & 1u) ^ 1u);
                 const uint32_t fb = smem_u32(&kv_full[s]);
                 mbar_arrive_expect_tx(fb, ATT_SMEM_STAGE);
-                tma_load_5d(sKV + s * ATT_SMEM_STAGE, tm, fb, 0, blk * ATT_BKEY, 0, h, b);
-                ++i;
-            };
-            for (int j = 0; j < AF_SLOTS && j < nkb; ++j) load(&tmap_k, j);
-            for (int j = 0; j < nkb; ++j) {
-                load(&tmap_v, j);
-                if (j + AF_SLOTS < nkb) load(&tmap_k, j + AF_SLOTS);
+                tma_load_5d(sKV + s * ATT_SMEM_STAGE, (i & 1) ? &tmap_v : &tmap_k, fb, 0, (i >> 1) * ATT_BKEY, 0, h, b);
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 9) {
+        // ===================== S issuer =====================
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, ATT_BKEY);
-        constexpr uint32_t idesc_o = umma_idesc_bf16(128, ATT_DH) | (1u << 16);  // B (V) MN-major; A (P) from TMEM, K-major
         mbar_wait(smem_u32(&q_full), 0);
         tc_fence_after();
-        const uint64_t q_hi = umma_desc_k_sw128(sQ), q_lo = umma_desc_k_sw128(sQ + ATT_TILE);
-        int i = 0;
-        auto issue_s = [&](int g) {
-            const int s = i % AF_STAGES, slot = g % AF_SLOTS;
-            mbar_wait(smem_u32(&kv_full[s]), (uint32_t)(i / AF_STAGES) & 1u);
+        if (lane == 0) att_trace(p, 1);
+        for (int g = 0; g < G; ++g) {
+            const int t = g % nt, j = g / nt, slot = g % AP_SLOTS;
+            const int i = 2 * j, ks = i % AP_STAGES;
+            if (t == 0) mbar_wait(smem_u32(&kv_full[ks]), (uint32_t)(i / AP_STAGES) & 1u);  // first use of K_j
+            if (g >= AP_SLOTS) mbar_wait(smem_u32(&pv_done[t]), (uint32_t)((g - AP_SLOTS) / nt) & 1u);  // PV_{g-2} has read the slot
             tc_fence_after();
             if (lane == 0) {
-                // slot reuse needs no barrier: S_g is issued after PV_{g-3}, which was issued after P_{g-3} was complete
-                // (softmax done with S_{g-3}) and reads P_{g-3} before this MMA writes (tcgen05.mma executes in issue order)
-                const uint32_t sk = sKV + s * ATT_SMEM_STAGE;
+                const uint32_t sq = sQ + t * ATT_SMEM_Q, sk = sKV + ks * ATT_SMEM_STAGE;
+                const uint64_t q_hi = umma_desc_k_sw128(sq), q_lo = umma_desc_k_sw128(sq + ATT_TILE);
                 const uint64_t k_hi = umma_desc_k_sw128(sk), k_lo = umma_desc_k_sw128(sk + ATT_TILE);
                 const uint32_t d_s = t_s + (uint32_t)(slot * ATT_BKEY);
 #pragma unroll
@@ -727,156 +747,177 @@ attention_flow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_lo + 2 * k, k_hi + 2 * k, idesc_s, 1u);
 #pragma unroll
                 for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_hi + 2 * k, k_lo + 2 * k, idesc_s, 1u);
-                umma_commit(smem_u32(&kv_empty[s]));
+                if (t == nt - 1) umma_commit(smem_u32(&kv_empty[ks]));  // last use of K_j
                 umma_commit(smem_u32(&s_full[slot]));
+                att_trace(p, 2 + 8 * g + 0);
             }
             __syncwarp();
-            ++i;
-        };
-        for (int g = 0; g < AF_SLOTS && g < nkb; ++g) issue_s(g);
-        for (int j = 0; j < nkb; ++j) {
-            const int s = i % AF_STAGES, slot = j % AF_SLOTS;
-            mbar_wait(smem_u32(&kv_full[s]), (uint32_t)(i / AF_STAGES) & 1u);
-            mbar_wait(smem_u32(&p_full[slot]), (uint32_t)(j / AF_SLOTS) & 1u);
+        }
+    } else if (warp == 10) {
+        // ===================== PV issuer =====================
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, 2 * ATT_DH) | (1u << 16);  // B = [V_hi | V_lo] MN-major; A (P) from TMEM
+        for (int g = 0; g < G; ++g) {
+            const int t = g % nt, j = g / nt, slot = g % AP_SLOTS;
+            const int i = 2 * j + 1, vs = i % AP_STAGES;
+            if (t == 0) mbar_wait(smem_u32(&kv_full[vs]), (uint32_t)(i / AP_STAGES) & 1u);  // first use of V_j
+            mbar_wait(smem_u32(&p_full[slot]), (uint32_t)(g / AP_SLOTS) & 1u);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t sv = sKV + s * ATT_SMEM_STAGE;
-                const uint64_t v_hi = umma_desc_mn_sw128(sv), v_lo = umma_desc_mn_sw128(sv + ATT_TILE);
-                const uint32_t a_hi = t_s + (uint32_t)(slot * ATT_BKEY), a_lo = a_hi + 64u;
+                const uint32_t sv = sKV + vs * ATT_SMEM_STAGE;
+                const uint64_t v_hi = umma_desc_mn_sw128(sv);
+                const uint32_t a0 = t_s + (uint32_t)(slot * ATT_BKEY), d_o = t_o + (uint32_t)(t * 2 * ATT_DH);
+                // The tensor-memory A operand is read at ~64 B/clk: a 128 x 16 P step costs 64 clk whatever N is, so both P
+                // planes run against the 128-wide B operand [V_hi | V_lo] (the lo tile is the next 64-wide N atom of the MN-major
+                // descriptor, 16 KB further): two passes of N = 128 instead of three of N = 64 - a third fewer P reads and MMA
+                // instructions, and the P_lo V_lo term comes for free.  O_t[:, 0:64] += P V_hi, O_t[:, 64:128] += P V_lo, summed
+                // in the epilogue.  k-step kk = 16 keys: P hi in 8 TMEM columns at 32 (kk / 2) + 8 (kk % 2) of the slot, lo 16
+                // columns further; V: 16 rows = 2048 B further per step
 #pragma unroll
-                for (int ks = 0; ks < ATT_BKEY / 16; ++ks)  // 16 keys = 8 TMEM columns of P, 16 rows (2048 B) of V
-                    umma_bf16_ts(t_o, a_hi + ks * 8, v_hi + (uint64_t)(ks * (2048 >> 4)), idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+                for (int kk = 0; kk < ATT_BKEY / 16; ++kk)
+                    umma_bf16_ts(d_o, a0 + (uint32_t)(32 * (kk >> 1) + 8 * (kk & 1)), v_hi + (uint64_t)(kk * (2048 >> 4)), idesc_o,
+                                 (j > 0 || kk > 0) ? 1u : 0u);
 #pragma unroll
-                for (int ks = 0; ks < ATT_BKEY / 16; ++ks)
-                    umma_bf16_ts(t_o, a_lo + ks * 8, v_hi + (uint64_t)(ks * (2048 >> 4)), idesc_o, 1u);
-#pragma unroll
-                for (int ks = 0; ks < ATT_BKEY / 16; ++ks)
-                    umma_bf16_ts(t_o, a_hi + ks * 8, v_lo + (uint64_t)(ks * (2048 >> 4)), idesc_o, 1u);
-                umma_commit(smem_u32(&kv_empty[s]));
-                umma_commit(smem_u32(&pv_done));
+                for (int kk = 0; kk < ATT_BKEY / 16; ++kk)
+                    umma_bf16_ts(d_o, a0 + (uint32_t)(32 * (kk >> 1) + 8 * (kk & 1) + 16), v_hi + (uint64_t)(kk * (2048 >> 4)), idesc_o, 1u);
+                if (t == nt - 1) umma_commit(smem_u32(&kv_empty[vs]));  // last use of V_j
+                umma_commit(smem_u32(&pv_done[t]));
+                att_trace(p, 2 + 8 * g + 1);
             }
             __syncwarp();
-            ++i;
-            if (j + AF_SLOTS < nkb) issue_s(j + AF_SLOTS);
         }
-    } else {
-        // ===================== softmax / correction / epilogue warps =====================
+    } else if ((warp >> 2) < nt) {
+        // ===================== softmax group t: one thread per query row =====================
+        const int t = warp >> 2;                  // query tile / group
         const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-        const int sub = (warp - 2) >> 2;          // 0/1: which 64 keys of every 128-key block this thread owns
         const int r = quarter * 32 + lane;        // row inside the tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-        float* xchg = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn)) + ATT_SMEM_Q + AF_STAGES * ATT_SMEM_STAGE);
+        const uint32_t t_orow = t_o + lane_off + (uint32_t)(t * 2 * ATT_DH);
         const float c = p.scale_log2e;
-        float mref = 0.f;                          // reference maximum of the raw logits (set by block 0)
+        const float2 c2 = make_float2(c, c);
+        float mref = __int_as_float(0xff800000);  // -inf: the first chunk of the row sets the reference
         float2 lsum2 = make_float2(0.f, 0.f);
         for (int j = 0; j < nkb; ++j) {
-            const int slot = j % AF_SLOTS;
-            mbar_wait(smem_u32(&s_full[slot]), (uint32_t)(j / AF_SLOTS) & 1u);
+            const int g = j * nt + t, slot = g % AP_SLOTS;
+            mbar_wait(smem_u32(&s_full[slot]), (uint32_t)(g / AP_SLOTS) & 1u);
             tc_fence_after();
             const uint32_t t_slot = t_s + lane_off + (uint32_t)(slot * ATT_BKEY);
-            uint32_t v[64];
-            {
-                uint32_t (&v0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[0]);
-                uint32_t (&v1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&v[32]);
-                tmem_ld_32x32(t_slot + (uint32_t)(sub * 64), v0);
-                tmem_ld_32x32(t_slot + (uint32_t)(sub * 64 + 32), v1);
+            bool waited_pv = false;  // pv_done[t] completes one phase per block; each thread observes phase j-1 exactly once in block j
+            uint32_t va[32], vb[32];
+            if ((threadIdx.x & 127) == 0) att_trace(p, 2 + 8 * g + 2);
+            tmem_ld_32x32(t_slot, va);
+            // one 32-key chunk: v holds S (fetched earlier), vn receives the next chunk while this one is exponentiated
+            auto chunk = [&](int k, uint32_t (&v)[32], uint32_t (&vn)[32]) {
                 tmem_ld_wait();
-            }
-            const int key0 = j * ATT_BKEY + sub * 64;
-            if (key0 + 64 > p.L) {  // ragged tail: keys beyond L do not take part
 #pragma unroll
-                for (int t = 0; t < 64; ++t)
-                    if (key0 + t >= p.L) v[t] = 0xff800000u;  // -inf
-            }
-            float bm = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+                for (int i2 = 0; i2 < 32; ++i2) asm volatile("" : "+r"(v[i2]));  // v is defined from here on, not earlier
+                if (k + 1 < ATT_BKEY / 32) tmem_ld_32x32(t_slot + (uint32_t)(32 * (k + 1)), vn);
+                const int key0 = j * ATT_BKEY + k * 32;
+                if (key0 + 32 > p.L) {  // ragged tail: keys beyond L do not take part
 #pragma unroll
-            for (int t = 2; t < 64; t += 2) bm = fmax3(bm, __uint_as_float(v[t]), __uint_as_float(v[t + 1]));
-            float* xb = xchg + (j & 1) * 256;
-            xb[sub * 128 + r] = bm;
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 softmax warps; also: both threads of a row hold their S in registers
-            bm = fmaxf(bm, xb[(sub ^ 1) * 128 + r]);
-            // pv_done completes one phase per PV_j.  A parity wait can only tell the current phase from the preceding one, so
-            // every thread observes the phases strictly in order: phase j-1 exactly once during block j - here if O must
-            // be rescaled, otherwise at the end of the block (by then PV_{j-1} has normally retired: no stall).
-            bool waited_pv = false;
-            if (j == 0) {
-                mref = bm;
-            } else {
-                const bool need = (bm - mref) * c > AF_TAU;
-                if (__any_sync(0xffffffffu, need)) {
-                    // slow path: move the reference and rescale what has been accumulated under the old one
-                    mbar_wait(smem_u32(&pv_done), (uint32_t)(j - 1) & 1u);
-                    waited_pv = true;
-                    tc_fence_after();
-                    const float f = need ? ex2f((mref - bm) * c) : 1.0f;
-                    uint32_t o[32];
-                    tmem_ld_32x32(t_o + lane_off + (uint32_t)(sub * 32), o);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * f);
-                    tmem_st_32x32(t_o + lane_off + (uint32_t)(sub * 32), o);
-                    lsum2.x *= f, lsum2.y *= f;
-                    if (need) mref = bm;
+                    for (int i2 = 0; i2 < 32; ++i2)
+                        if (key0 + i2 >= p.L) v[i2] = 0xff800000u;  // -inf
                 }
-            }
-            const float2 c2 = make_float2(c, c);
-            const float2 nm2 = make_float2(-mref * c, -mref * c);
+                float cm = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                uint32_t hi[16], lo[16];
+                for (int i2 = 2; i2 < 32; i2 += 2) cm = fmax3(cm, __uint_as_float(v[i2]), __uint_as_float(v[i2 + 1]));
+                const bool need = (cm - mref) * c > AP_TAU;  // false for a fully masked chunk (cm = -inf)
+                if (__any_sync(0xffffffffu, need)) {
+                    // move the reference of the rows that need it; everything accumulated under the old one is rescaled
+                    const float f = need ? ex2f((mref - cm) * c) : 1.0f;  // first chunk of a row: mref = -inf -> f = 0
+                    tmem_st_wait();  // P chunks written above are re-read below
+                    if (j > 0) {
+                        if (!waited_pv) mbar_wait(smem_u32(&pv_done[t]), (uint32_t)(j - 1) & 1u);
+                        waited_pv = true;
+                        tc_fence_after();
+#pragma unroll 1
+                        for (int hh = 0; hh < 4; ++hh) {
+                            uint32_t o[32];
+                            tmem_ld_32x32(t_orow + (uint32_t)(hh * 32), o);
+                            tmem_ld_wait();
 #pragma unroll
-                for (int t = 0; t < 32; t += 2) {
-                    const float2 x = ffma2(make_float2(__uint_as_float(v[hh * 32 + t]), __uint_as_float(v[hh * 32 + t + 1])), c2, nm2);
+                            for (int i2 = 0; i2 < 32; ++i2) o[i2] = __float_as_uint(__uint_as_float(o[i2]) * f);
+                            tmem_st_32x32(t_orow + (uint32_t)(hh * 32), o);
+                        }
+                    }
+#pragma unroll 1
+                    for (int kk = 0; kk < k; ++kk) {  // chunks of this block already written as P under the old reference
+                        uint32_t pk[32];
+                        tmem_ld_32x32(t_slot + (uint32_t)(32 * kk), pk);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i2 = 0; i2 < 16; ++i2) {
+                            const float e0 = (bf16lo_f(pk[i2]) + bf16lo_f(pk[16 + i2])) * f;
+                            const float e1 = (bf16hi_f(pk[i2]) + bf16hi_f(pk[16 + i2])) * f;
+                            uint32_t h2, l2;
+                            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(e1), "f"(e0));
+                            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(e1 - bf16hi_f(h2)), "f"(e0 - bf16lo_f(h2)));
+                            pk[i2] = h2, pk[16 + i2] = l2;
+                        }
+                        tmem_st_32x32(t_slot + (uint32_t)(32 * kk), pk);
+                    }
+                    lsum2.x *= f, lsum2.y *= f;
+                    if (need) mref = cm;
+                    // (the tcgen05.wait::ld above also completed the prefetch of the next chunk: harmless)
+                }
+                const float2 nm2 = make_float2(-mref * c, -mref * c);
+                uint32_t hl[32];  // hi pairs in [0,16), lo pairs in [16,32)
+#pragma unroll
+                for (int i2 = 0; i2 < 32; i2 += 2) {
+                    const float2 x = ffma2(make_float2(__uint_as_float(v[i2]), __uint_as_float(v[i2 + 1])), c2, nm2);
                     const float2 e = make_float2(ex2f(x.x), ex2f(x.y));
                     lsum2 = fadd2(lsum2, e);
                     uint32_t h2;
                     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(e.y), "f"(e.x));
-                    const float2 hf = make_float2(__uint_as_float(h2 << 16), __uint_as_float(h2 & 0xffff0000u));
-                    const float2 d = fsub2(e, hf);
+                    const float2 d = fsub2(e, make_float2(bf16lo_f(h2), bf16hi_f(h2)));
                     uint32_t l2;
                     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(l2) : "f"(d.y), "f"(d.x));
-                    hi[t >> 1] = h2;
-                    lo[t >> 1] = l2;
+                    hl[i2 >> 1] = h2;
+                    hl[16 + (i2 >> 1)] = l2;
                 }
-                // keys [64 sub + 32 hh, +32) of the block: 16 columns of the hi half / the lo half of the slot
-                tmem_st_32x16(t_slot + (uint32_t)(sub * 32 + hh * 16), hi);
-                tmem_st_32x16(t_slot + 64u + (uint32_t)(sub * 32 + hh * 16), lo);
-            }
-            if (j > 0 && !waited_pv) mbar_wait(smem_u32(&pv_done), (uint32_t)(j - 1) & 1u);
+                tmem_st_32x32(t_slot + (uint32_t)(32 * k), hl);  // in place: the 32 columns this chunk's S came from
+            };
+            chunk(0, va, vb);
+            if ((threadIdx.x & 127) == 0) att_trace(p, 2 + 8 * g + 3);
+            chunk(1, vb, va);
+            chunk(2, va, vb);
+            chunk(3, vb, va);
+            if ((threadIdx.x & 127) == 0) att_trace(p, 2 + 8 * g + 4);
+            if (j > 0 && !waited_pv) mbar_wait(smem_u32(&pv_done[t]), (uint32_t)(j - 1) & 1u);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(smem_u32(&p_full[slot]));
+            if ((threadIdx.x & 127) == 0) att_trace(p, 2 + 8 * g + 5);
         }
-        // ---- epilogue: O / rowsum -> split-bf16 [B*L, H*dh]; thread `sub` stores 32 of the 64 columns ----
-        float lsum = lsum2.x + lsum2.y;
-        float* xb = xchg + (nkb & 1) * 256;
-        xb[sub * 128 + r] = lsum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        lsum += xb[(sub ^ 1) * 128 + r];
-        mbar_wait(smem_u32(&pv_done), (uint32_t)(nkb - 1) & 1u);
+        // ---- epilogue: O_t / rowsum -> split-bf16 [B*L, H*dh] ----
+        const float lsum = lsum2.x + lsum2.y;
+        mbar_wait(smem_u32(&pv_done[t]), (uint32_t)(nkb - 1) & 1u);
         tc_fence_after();
-        const int qrow = q_tile * ATT_BQ + r;
+        const int qrow = (q_tile0 + t) * ATT_BQ + r;
         const float inv = 1.0f / lsum;
         __nv_bfloat16* ohi = p.out_hi + (long long)b * p.out_b + (long long)h * p.out_h + (long long)qrow * p.ldo;
         __nv_bfloat16* olo = ohi + p.out_plane;
-        {
-            uint32_t o[32];
-            tmem_ld_32x32(t_o + lane_off + (uint32_t)(sub * 32), o);
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[32], o2[32];
+            tmem_ld_32x32(t_orow + (uint32_t)(hh * 32), o);             // P V_hi
+            tmem_ld_32x32(t_orow + (uint32_t)(ATT_DH + hh * 32), o2);   // P V_lo
             tmem_ld_wait();
+#pragma unroll
+            for (int i2 = 0; i2 < 32; ++i2) o[i2] = __float_as_uint(__uint_as_float(o[i2]) + __uint_as_float(o2[i2]));
             if (qrow < p.L) {
 #pragma unroll
-                for (int t = 0; t < 32; t += 8) {
-                    uint32_t hh[4], ll[4];
+                for (int i2 = 0; i2 < 32; i2 += 8) {
+                    uint32_t oh[4], ol[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         __nv_bfloat16 h0, l0, h1, l1;
-                        split_bf16(__uint_as_float(o[t + 2 * u]) * inv, h0, l0);
-                        split_bf16(__uint_as_float(o[t + 2 * u + 1]) * inv, h1, l1);
-                        hh[u] = pack_bf16x2(h0, h1);
-                        ll[u] = pack_bf16x2(l0, l1);
+                        split_bf16(__uint_as_float(o[i2 + 2 * u]) * inv, h0, l0);
+                        split_bf16(__uint_as_float(o[i2 + 2 * u + 1]) * inv, h1, l1);
+                        oh[u] = pack_bf16x2(h0, h1);
+                        ol[u] = pack_bf16x2(l0, l1);
                     }
-                    *reinterpret_cast<uint4*>(ohi + sub * 32 + t) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-                    *reinterpret_cast<uint4*>(olo + sub * 32 + t) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                    *reinterpret_cast<uint4*>(ohi + hh * 32 + i2) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                    *reinterpret_cast<uint4*>(olo + hh * 32 + i2) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
                 }
             }
         }
@@ -884,7 +925,8 @@ attention_flow_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (threadIdx.x == 0) att_trace(p, 200);
+    if (warp == 9) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -895,6 +937,9 @@ int make_operand_map_ext(CUtensorMap* map, const psam_operand* op, int box_rows,
 }  // namespace psam
 
 namespace psam {
+
+static unsigned long long* g_attention_trace = nullptr;  // tools/attention_trace.py only (psam_debug_attention_trace)
+static int g_attention_tiles_per_cta = 2;                // experiment switch (psam_debug_attention_tiles): 1 or 2 query tiles per CTA
 
 static int attention_setup(const psam_operand* q, const psam_operand* k, const psam_operand* v, void* out_hi, long long out_plane,
                            long long ldo, long long out_head_stride, long long out_cloud_stride, float scale, CUtensorMap* mq,
@@ -915,11 +960,16 @@ static int attention_setup(const psam_operand* q, const psam_operand* k, const p
     p->scale_log2e = scale * 1.4426950408889634f;
     p->out_hi = (__nv_bfloat16*)out_hi;
     p->out_plane = out_plane, p->ldo = ldo, p->out_h = out_head_stride, p->out_b = out_cloud_stride;
+    p->trace = g_attention_trace;
+    p->tiles_per_cta = g_attention_tiles_per_cta;
     *grid = dim3((unsigned)ceil_div(L, ATT_BQ), (unsigned)H, (unsigned)B);
     return PSAM_OK;
 }
 
 }  // namespace psam
+
+extern "C" void psam_debug_attention_trace(unsigned long long* device_buffer) { psam::g_attention_trace = device_buffer; }
+extern "C" void psam_debug_attention_tiles(int tiles_per_cta) { psam::g_attention_tiles_per_cta = tiles_per_cta == 1 ? 1 : 2; }
 
 extern "C" int psam_attention_bf16x3(const psam_operand* q, const psam_operand* k, const psam_operand* v, void* out_hi,
                                      long long out_plane, long long ldo, long long out_head_stride,
@@ -930,8 +980,9 @@ extern "C" int psam_attention_bf16x3(const psam_operand* q, const psam_operand* 
     dim3 grid;
     int rc = attention_setup(q, k, v, out_hi, out_plane, ldo, out_head_stride, out_cloud_stride, scale, &mq, &mk, &mv, &p, &grid);
     if (rc) return rc;
-    PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AF_SMEM_TOTAL));
-    PSAM_CUDA_TRY(psam::launch(attention_flow_kernel, dim3(grid), dim3(ATT_THREADS), (size_t)(AF_SMEM_TOTAL), stream, mq, mk, mv, p));
+    grid.x = (grid.x + p.tiles_per_cta - 1) / p.tiles_per_cta;  // one or two query tiles per CTA
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM_TOTAL));
+    PSAM_CUDA_TRY(psam::launch(attention_pair_kernel, dim3(grid), dim3(AP_THREADS), (size_t)(AP_SMEM_TOTAL), stream, mq, mk, mv, p));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }

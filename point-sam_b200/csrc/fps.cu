@@ -48,6 +48,7 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long 
     __shared__ __align__(16) uint4 slot_a[2][FPS_MAX_SLOTS];  // records received from every warp of the cluster {bits, prio, x, y}
     __shared__ float slot_z[2][FPS_MAX_SLOTS];
     __shared__ __align__(8) uint64_t mbar[2];
+    extern __shared__ float spts[];  // PPT > 0: this CTA's points, [slot][thread][xyz] - the winning lane fetches its candidate by index
 
     const uint32_t C = cluster_nctarank();
     const uint32_t rank = cluster_ctarank();
@@ -58,6 +59,12 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long 
     const int stride = (int)C * FPS_THREADS;
     const int gt = (int)rank * FPS_THREADS + tid;
     const uint32_t tx_bytes = C * FPS_WARPS * 20u;  // every warp of every peer (incl. this CTA) delivers 16 + 4 bytes per iteration
+    // When the thread stride is a multiple of T, (j mod T) is the same for every point of a thread and (j div T) grows with the
+    // slot: the tie-break priority is prio0 + slot * kprio, i.e. among equal maxima of ONE thread the lowest slot wins.  The
+    // per-iteration tie scan then needs no priority arithmetic at all (it was ~45 % of the loop's instructions).
+    const bool linear_prio = (stride & (int)tmask) == 0;
+    const uint32_t prio0 = fps_prio((uint32_t)gt, tmask, log2T);
+    const uint32_t kprio = (uint32_t)stride >> log2T;
 
     xyz += (size_t)cloud * N * 3;
     idx_out += (size_t)cloud * G;
@@ -86,6 +93,9 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long 
                 px[s] = py[s] = pz[s] = 0.0f;
                 md[s] = 0.0f;  // never a candidate unless everything is 0 (then the result is ignored)
             }
+            spts[(s * FPS_THREADS + tid) * 3 + 0] = px[s];
+            spts[(s * FPS_THREADS + tid) * 3 + 1] = py[s];
+            spts[(s * FPS_THREADS + tid) * 3 + 2] = pz[s];
         }
     } else {
         for (int j = gt; j < N; j += stride) md_g[j] = __int_as_float(0x7f800000);
@@ -131,7 +141,17 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long 
         const uint32_t bestbits = __float_as_uint(best);
         const uint32_t wmax = __reduce_max_sync(0xffffffffu, bestbits);
         if constexpr (PPT > 0) {
-            if (bestbits == wmax) {
+            if (linear_prio) {
+                int bs = PPT;  // lowest slot holding the warp maximum (PPT = none)
+#pragma unroll
+                for (int s = PPT - 1; s >= 0; --s)
+                    if (__float_as_uint(md[s]) == wmax) bs = s;
+                if (bs < PPT) {
+                    myprio = prio0 + (uint32_t)bs * kprio;
+                    const float* c = spts + (bs * FPS_THREADS + tid) * 3;  // own data: written by this thread before the loop
+                    wx = c[0], wy = c[1], wz = c[2];
+                }
+            } else if (bestbits == wmax) {
 #pragma unroll
                 for (int s = 0; s < PPT; ++s) {
                     const uint32_t pr = fps_prio((uint32_t)(s * stride + gt), tmask, log2T);
@@ -167,8 +187,10 @@ fps_cluster_kernel(const float* __restrict__ xyz, int N, int G, int log2T, long 
         {
             const uint32_t bar = smem_u32(&mbar[p]);
             const uint32_t parity = ((uint32_t)(it - 1) >> 1) & 1u;
-            while (!mbar_try_wait_acquire_cluster(bar, parity)) {
-            }
+            // the records arrive through st.async + complete_tx: the phase completion itself orders them before this
+            // wait returns (as for TMA writes); a cluster-scope acquire would add an L1 invalidation (CCTL.IVALL, 19 % of
+            // the kernel's stall samples in profiles/r02) to every iteration
+            mbar_wait(bar, parity);
             if (tid == 0) mbar_arrive_expect_tx(bar, tx_bytes);
         }
         // ---- 5. reduce the records (every warp redundantly; lane l folds records l, l+32, ...) ------
@@ -209,7 +231,9 @@ static int launch_fps(const float* xyz, int B, int N, int G, int log2T, long lon
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * cluster));
     cfg.blockDim = dim3(FPS_THREADS);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = (size_t)PPT * FPS_THREADS * 3 * sizeof(float);
+    if (cfg.dynamicSmemBytes > 32 * 1024)  // static + dynamic beyond the 48 KB default needs the opt-in
+        PSAM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -1149,10 +1149,12 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
             return launch_gemm_persist<64, 4, 64, 1>(ma, mb, sh, ep, ctas, stream);
         }
     }
-    // wide tiles, throughput policy: the dual-resident configuration (two 97 KB CTAs per SM, BK = 32, 2 stages each);
-    // GV_DUAL forces it for any wide tile, GV_NO_DUAL keeps the one-CTA-per-SM kernel.
+    // wide tiles: the dual-resident configuration (two 97 KB CTAs per SM, BK = 32, 2 stages each) on request (GV_DUAL).
     // GV_BK32: one CTA per SM with 4 half-size stages.  MEASURED round 1: 611 vs 618 clouds/s - no gain, opt-in.
-    const bool dual = bn > 160 && cm == 1 && ((variant & GV_DUAL) || (o->tile_hint == 1 && !(variant & GV_NO_DUAL)));
+    // MEASURED round 2 (c2, 8 clouds in flight, 3 repeats): dual-resident 606 / 644 clouds/s (LN-free / LayerNorm blocks) vs
+    // 642 / 635 for the one-CTA-per-SM kernel, and +1.8 ms single-stream latency: with two 2-stage CTAs per SM neither can hide
+    // the operand latency alone while the other is in its prologue / epilogue.  Opt-in (GV_DUAL) only.
+    const bool dual = bn > 160 && cm == 1 && (variant & GV_DUAL) && !(variant & GV_NO_DUAL);
     if (bn > 160 && cm == 1 && (dual || (variant & GV_BK32))) {
         rc = make_operand_map(&ma, a, GEMM_BM, passes == 3 ? 2 : 1, 32);
         if (rc) return rc;

@@ -281,3 +281,4 @@ def split_f32(x: torch.Tensor, out: Split, add: Optional[torch.Tensor] = None):
     else:
         nv.check(nv.lib().psam_split_add_f32(nv.ptr(x), nv.ptr(add), x.shape[-1], rows, x.shape[-1], out.ptr(), out.plane, out.pitch,
                                              out.pitch, nv.stream()), "split_add_f32")
+

@@ -538,19 +538,22 @@ def test_fused_attention_tc(B, H, L, entry):
     assert err < 5e-5 * max(1.0, float(want.abs().max())), err
 
 
-@pytest.mark.parametrize("L", [512, 1100])
-def test_fused_attention_tc_reference_maximum_moves(L):
-    """Logits that grow from key block to key block (by far more than the 2^8 slack) force the rare slow path of the
-    streaming kernel: the reference maximum moves and O is rescaled in tensor memory - several times per row, for a
-    subset of rows only (rows whose query is negated see DEcreasing logits and never rescale)."""
+@pytest.mark.parametrize("L,step,gain", [(512, 128, 2.0), (1100, 128, 2.0), (512, 32, 4.5), (700, 32, 4.5), (300, 32, 4.5)])
+def test_fused_attention_tc_reference_maximum_moves(L, step, gain):
+    """Logits that grow along the keys (by far more than the 2^40 slack of the lazy reference maximum) force the rare slow
+    path of the streaming kernel: the reference moves and the owning thread rescales O in tensor memory, its running sum
+    and - when the jump happens between two 32-key chunks of one block (step = 32) - the P chunks of the current block it
+    has already written.  Only a subset of rows is affected (rows whose query is negated see DEcreasing logits)."""
     B, H, dh = 1, 2, 64
     D = H * dh
     g = torch.Generator(device="cpu").manual_seed(5)
     qkv = torch.randn(B * L, 3 * D, generator=g)
-    ramp = (torch.arange(L) // 128).float()[:, None]            # key block index
+    ramp = (torch.arange(L) // step).float()[:, None]           # key block (or 32-key chunk) index
+    if step == 32:  # three jumps in a row, at chunks 6, 7, 8: inside block 1 and at the start of block 2 (logits stay moderate)
+        ramp = (ramp - 5.0).clamp(0.0, 3.0)
     qkv[:, :D] = torch.randn(L, D, generator=g) * 0.2 + 1.0     # queries: common positive direction ...
     qkv[::3, :D] *= -1.0                                         # ... every third row negated
-    qkv[:, D:2 * D] = torch.randn(L, D, generator=g) * 0.2 + 2.0 * ramp  # keys grow with the block index
+    qkv[:, D:2 * D] = torch.randn(L, D, generator=g) * 0.2 + gain * ramp  # keys grow with the block / chunk index
     qkv = qkv.to(_dev())
     got, want = _attention_case(qkv, B, H, L, "psam_attention_bf16x3")
     err = float((got - want).abs().max())
