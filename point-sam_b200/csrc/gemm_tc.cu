@@ -1091,7 +1091,13 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     const int mtiles = ceil_div(sh.M, GEMM_BM);
     // 2-CTA path (cta_group::2): pairs of m-tiles, each CTA streams half of the W tile.  Opt-in: variant bit 0x1.
     {
-        const int use2 = variant & GV_2CTA;
+        // Throughput policy with many rows (>= 16 m-tiles: several clouds per request) and deep K: the pair halves the W bytes
+        // each SM ingests.  MEASURED round 2: c3 (4 clouds per graph, M = 2048) 444 -> 474 clouds/s; c2 (M = 512) 694 -> 682, so
+        // single-cloud requests keep the 1-CTA kernel.  Launches with >= 2 tiles per SM go to the persistent kernel below.
+        const long long tiles256 = (long long)ceil_div(sh.N, 256) * mtiles * sh.nb1 * sh.nb2 * sh.split_k;
+        const bool auto2 = o->tile_hint == 1 && mtiles >= 16 && sh.K >= 1024 && sh.N >= 256 && tiles256 < 2 * 148 &&
+                           !(variant & (GV_PERSIST | GV_DUAL | GV_BK32 | GV_NO_DUAL)) && ((variant >> 8) & 15) == 0;
+        const int use2 = (variant & GV_2CTA) || auto2;
         if (use2 && mtiles >= 2 && sh.N >= 128) {
             int bn2 = (o->tile_hint == 1 || sh.N >= 256) ? 256 : 128;
             if (o->tile_hint >= 64 && o->tile_hint <= 256 && o->tile_hint % 64 == 0) bn2 = o->tile_hint;
@@ -1144,6 +1150,9 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
             if (rc) return rc;
             rc = make_operand_map(&mb, w, bn, passes == 3 ? 2 : 1, bkp);
             if (rc) return rc;
+            // short main loops (the mini-PointNet: K = 128 ... 512) are bounded by the epilogue: eight epilogue warps and
+            // three stages; long ones by operand latency: four stages, four epilogue warps
+            if (bn > 128 && sh.K <= 512) return launch_gemm_persist<256, 3, 32, 2>(ma, mb, sh, ep, ctas, stream);
             if (bn > 128) return launch_gemm_persist<256, 4, 32, 1>(ma, mb, sh, ep, ctas, stream);
             if (bn > 64) return launch_gemm_persist<128, 3, 64, 1>(ma, mb, sh, ep, ctas, stream);
             return launch_gemm_persist<64, 4, 64, 1>(ma, mb, sh, ep, ctas, stream);

@@ -96,6 +96,48 @@ __device__ uint32_t kth_smallest_radix(const float* vals, int n, int k, int* his
     return prefix;
 }
 
+// Upper bound of the k-th smallest of vals[0..n) from ONE histogram pass over the digit [30:20] (exponent + 3 mantissa bits):
+// the upper edge of the bin that holds the k-th element.  At most 12.5 % above the k-th value - good enough for the
+// candidate filter of phase A (a looser tau only admits a few more candidates), at a third of the passes and barriers of
+// the exact select.
+__device__ uint32_t kth_upper_bound_hist(const float* vals, int n, int k, int* hist) {
+    __shared__ int s_warp_tot2[KNN_THREADS / 32];
+    __shared__ int s_digit2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nb = 2048, per = nb / KNN_THREADS;
+    __syncthreads();
+    for (int i = tid; i < nb; i += KNN_THREADS) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += KNN_THREADS) atomicAdd(&hist[__float_as_uint(vals[i]) >> 20], 1);
+    __syncthreads();
+    int local = 0;
+#pragma unroll
+    for (int t = 0; t < per; ++t) local += hist[tid * per + t];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_tot2[warp] = incl;
+    __syncthreads();
+    int before = incl - local;
+    for (int w = 0; w < warp; ++w) before += s_warp_tot2[w];
+    if (before < k && k <= before + local) {  // exactly one thread
+        int run = before;
+        for (int t = 0; t < per; ++t) {
+            run += hist[tid * per + t];
+            if (k <= run) {
+                s_digit2 = tid * per + t;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t edge = ((uint32_t)s_digit2 << 20) | 0xFFFFFu;
+    return edge < 0x7F800000u ? edge : 0x7F7FFFFFu;  // never a NaN / inf pattern: the sweep compares tau as a float
+}
+
 // One CTA serves C consecutive query centres of one cloud.
 //   A. per centre: squared distances to a strided SAMPLE of the keys -> exact K-th smallest of the sample (radix select)
 //      = tau_c, an upper bound of the true K-th distance.
@@ -124,8 +166,8 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ key, int Q
            int sample_cap, int cap, long long* __restrict__ idx_out, float* __restrict__ d2_out) {
     pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_sample = reinterpret_cast<float*>(smem_raw);       // [sample_cap]
-    float* c_d2_all = s_sample + sample_cap;                    // [C][cap]
+    float* s_sample = reinterpret_cast<float*>(smem_raw);       // [C][sample_cap]
+    float* c_d2_all = s_sample + (size_t)C * sample_cap;        // [C][cap]
     int* c_idx_all = reinterpret_cast<int*>(c_d2_all + (size_t)C * cap);  // [C][cap]
     int* cnt = c_idx_all + (size_t)C * cap;                     // [64]
     int* hist = cnt + 64;                                       // [KNN_HIST]
@@ -147,18 +189,33 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ key, int Q
     zero_counters(cnt);
 
     // ---- A. sample bound per centre ------------------------------------------------------------
+    // the strided sample is loaded ONCE for the C centres, eight points per thread at a time with all 24 loads in flight
+    // (the loop used to expose one L2 round trip per sample and per centre)
     const int ns = (N + sample_stride - 1) / sample_stride;
+    for (int i0 = 0; i0 < ns; i0 += 8 * KNN_THREADS) {
+        float sx[8], sy[8], sz[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * KNN_THREADS + tid;
+            const size_t j = (size_t)min(i, ns - 1) * sample_stride;
+            sx[u] = key[j * 3], sy[u] = key[j * 3 + 1], sz[u] = key[j * 3 + 2];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * KNN_THREADS + tid;
+            if (i < ns) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) s_sample[(size_t)c * sample_cap + i] = sqdist3(sx[u], sy[u], sz[u], cx[c], cy[c], cz[c]);
+            }
+        }
+    }
+    __syncthreads();
 #pragma unroll 1
     for (int c = 0; c < C; ++c) {
-        for (int i = tid; i < ns; i += KNN_THREADS) {
-            const size_t j = (size_t)i * sample_stride;
-            s_sample[i] = sqdist3(key[j * 3], key[j * 3 + 1], key[j * 3 + 2], cx[c], cy[c], cz[c]);
-        }
-        __syncthreads();
-        const uint32_t t = kth_smallest_radix(s_sample, ns, K, hist);
+        const uint32_t t = kth_upper_bound_hist(s_sample + (size_t)c * sample_cap, ns, K, hist);
         if (tid == 0) s_tau[c] = t;
-        __syncthreads();
     }
+    __syncthreads();
     uint32_t tau[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) tau[c] = s_tau[c];
@@ -357,16 +414,26 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ key, int Q
             }
         }
         __syncthreads();
-        for (int i = tid; i < K; i += KNN_THREADS) {
-            const uint32_t u = __float_as_uint(f_d2[i]);
-            const int ji = f_idx[i];
+        // rank of every winner among the K by (d2, index): four lanes per winner, each over a quarter of the list
+        for (int i0 = 0; i0 < K; i0 += KNN_THREADS / 4) {
+            const int i = i0 + (tid >> 2), part = tid & 3;
             int rank = 0;
-            for (int t = 0; t < K; ++t) {
-                const uint32_t ut = __float_as_uint(f_d2[t]);
-                rank += (ut < u) || (ut == u && f_idx[t] < ji);
+            uint32_t u = 0;
+            int ji = 0;
+            if (i < K) {
+                u = __float_as_uint(f_d2[i]);
+                ji = f_idx[i];
+                for (int t = part; t < K; t += 4) {
+                    const uint32_t ut = __float_as_uint(f_d2[t]);
+                    rank += (ut < u) || (ut == u && f_idx[t] < ji);
+                }
             }
-            idx_out[((size_t)b * Q + q) * K + rank] = ji;
-            if (d2_out) d2_out[((size_t)b * Q + q) * K + rank] = f_d2[i];
+            rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+            rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+            if (i < K && part == 0) {
+                idx_out[((size_t)b * Q + q) * K + rank] = ji;
+                if (d2_out) d2_out[((size_t)b * Q + q) * K + rank] = __uint_as_float(u);
+            }
         }
         __syncthreads();  // f_d2 / f_idx (the sample area) are reused by the next centre
     }
@@ -690,7 +757,7 @@ extern "C" int psam_knn_f32(const float* query, const float* key, int B, int Q, 
     if (cap < K) return PSAM_ERR_UNSUPPORTED;
     // centres per CTA: as many as keep >= 1.5 CTAs per SM (the per-centre select phases are latency-bound: they need
     // co-resident CTAs to overlap) and fit two CTAs' shared memory on an SM
-    auto smem_for = [&](int c) { return (size_t)sample_cap * 4 + (size_t)c * cap * 8 + (64 + KNN_HIST) * 4; };
+    auto smem_for = [&](int c) { return (size_t)c * sample_cap * 4 + (size_t)c * cap * 8 + (64 + KNN_HIST) * 4; };
     int C = 4;
     while (C > 1 && ((long long)B * ((Q + C - 1) / C) < 222 || smem_for(C) > 100 * 1024)) C /= 2;
     const size_t smem = smem_for(C);

@@ -393,7 +393,7 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int, fold=N
     H, dh = pb.H, pb.dh
     qkv = Split(M, 3 * D, dev)
     if fold is not None:
-        xs, st_in, st_mid, st_out = fold
+        xs, st_in, st_mid, st_out = fold[:4]
         ops.gemm(xs, pb.wqkv_f, bias=pb.bqkv_f, out_split=qkv, passes=PASSES, ln_fold=(st_in, pb.cqkv, D, pb.eps1))
     else:
         xn = Split(M, D, dev)
@@ -414,7 +414,7 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int, fold=N
     if fold is not None:
         # one writer per element (no split-K): the epilogue also emits split-bf16(x) and the row statistics for norm2
         ops.gemm(att, pb.wproj, bias=pb.bproj, out_f32=x, resid=x, out_split=xs, stats_out=st_mid, passes=PASSES)
-        _run_mlp_folded(pb, x, xs, st_mid, st_out, M, D, dev)
+        _run_mlp_folded(pb, x, xs, st_mid, st_out, M, D, dev, stats=fold[4] if len(fold) > 4 else None)
         return
     sk = _split_k_for(M, D, D)
     if sk > 1:
@@ -446,12 +446,13 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, L: int, D: int, fold=N
         ops.gemm(h, pb.w2, bias=pb.bb2, out_f32=x, resid=x, passes=PASSES, ln_fold=fold)
 
 
-def _run_mlp_folded(pb: _PackedBlock, x, xs, st_mid, st_out, M, D, dev):
+def _run_mlp_folded(pb: _PackedBlock, x, xs, st_mid, st_out, M, D, dev, stats=None):
     """x += mlp(norm2(x)) with norm2 folded into fc1 (and SwiGLU.norm into fc2); fc2 refreshes xs and st_out."""
     if pb.swiglu:
         if not pb.fold_ln:
             raise RuntimeError("PSAM_FUSED_BLOCK_LN requires PSAM_FUSED_INNER_LN")
-        stats = torch.zeros((M, 2), dtype=torch.float32, device=dev)
+        if stats is None:
+            stats = torch.zeros((M, 2), dtype=torch.float32, device=dev)
         h = Split(M, pb.hp, dev, pitch=pb.hp)
         ops.gemm(xs, pb.w1_f, bias=pb.bb1_f, out_split=h, passes=PASSES, swiglu=True, stats_out=stats,
                  ln_fold=(st_mid, pb.c1, D, pb.eps2))
@@ -479,11 +480,12 @@ def run_pc_encoder(enc, coords, features):
         # LayerNorm-free encoder: every GEMM that writes the residual stream also writes its split-bf16 copy and row
         # statistics; norm1 / norm2 / fc_norm are applied inside the consuming GEMMs' epilogues
         nb = len(pk.blocks)
-        st = torch.zeros((2 * nb + 1, M, 2), dtype=torch.float32, device=dev)  # one memset for all statistics of the step
+        # one memset for all row statistics of the step: residual stream (2 nb + 1) and SwiGLU hidden rows (nb)
+        st = torch.zeros((3 * nb + 1, M, 2), dtype=torch.float32, device=dev)
         xs = Split(M, D, dev)
         ops.gemm(pos, pk.wpos2, bias=pk.bpos2, out_f32=x, resid=x, out_split=xs, stats_out=st[0], passes=PASSES)
         for i, pb in enumerate(pk.blocks):
-            _run_block(pb, x, B, L, D, fold=(xs, st[2 * i], st[2 * i + 1], st[2 * i + 2]))
+            _run_block(pb, x, B, L, D, fold=(xs, st[2 * i], st[2 * i + 1], st[2 * i + 2], st[2 * nb + 1 + i]))
         out = torch.empty((B, L, enc.embed_dim), dtype=torch.float32, device=dev)
         ops.gemm(xs, pk.wout_f, bias=pk.bout_f, out_f32=out.view(M, -1), passes=PASSES,
                  ln_fold=(st[2 * nb], pk.cout, D, pk.eps_tail))

@@ -68,7 +68,8 @@ def bench(name, M, N, K, variant, hint, sk=1, concurrent=1, swiglu=False, reps=3
 VARIANTS = [("oneshot", ops.GV_NO_DUAL | ops.GV_NO_PERSIST), ("dual", ops.GV_DUAL | ops.GV_NO_PERSIST), ("2cta", ops.GV_2CTA | ops.GV_NO_PERSIST),
             ("persist", ops.GV_PERSIST)]
 quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
-for M, conc in ([(4096, 1), (512, 8)] if quick else [(512, 1), (512, 8), (2048, 2), (4096, 1), (4096, 2)]):
+pe_only = len(sys.argv) > 1 and sys.argv[1] == "pe"
+for M, conc in [] if pe_only else ([(4096, 1), (512, 8)] if quick else [(512, 1), (512, 8), (2048, 2), (4096, 1), (4096, 2)]):
     for nm, (N, K, sw) in {"qkv": (3072, 1024, False), "proj": (1024, 1024, False), "fc1sw": (5504, 1024, True), "fc2": (1024, 2752, False)}.items():
         for vn, var in VARIANTS:
             try:

@@ -44,7 +44,7 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
 fam = {}
 for k, a in agg.items():
     n = k[0]
-    f_ = ("GEMM (tcgen05)" if "gemm_tc" in n else "fused attention (tcgen05)" if "attention_tc" in n else "FPS" if "fps" in n else
+    f_ = ("GEMM (tcgen05)" if "gemm_tc" in n else "fused attention (tcgen05)" if ("attention_tc" in n or "attention_pair" in n or "attention_flow" in n) else "FPS" if "fps" in n else
           "kNN / gathers / interp" if ("knn" in n or "gather" in n or "border" in n) else "LayerNorm family" if ("layernorm" in n or "swiglu" in n or "interp_ln" in n) else
           "decoder SIMT (linear / small attention)" if ("linear" in n or "attention_small" in n or "decoder" in n) else "other")
     b = fam.setdefault(f_, [0.0, 0.0, 0])
