@@ -354,7 +354,8 @@ def run_c3(name, args, model, dev, dist, rank, world, barrier):
     n_chunks = n_local // max(1, chunk)
     saved = model.prompt_iters
     model.prompt_iters = iters
-    lanes = [model.make_iterative_predictor(chunk, M, N, use_graph=not args.no_graph) for _ in range(min(n_chunks, args.c3_lanes))]
+    n_lanes = min(n_chunks, args.c3_lanes)
+    lanes = [model.make_iterative_predictor(chunk, M, N, use_graph=not args.no_graph, throughput_tiles=n_lanes > 1) for _ in range(n_lanes)]
     host = []
     for ci in range(n_chunks):
         xyz = torch.cat([synth.make_batch(1, N, 5000 + lo + ci * chunk + b, "ball")[0] for b in range(chunk)])

@@ -52,9 +52,26 @@ int psam_knn_f32(const float* query, const float* key, int B, int Q, int N, int 
 
 /* Group-feature gather: groups[b2,g,k,:] = [(xyz[b,idx]-centers[b,g])/radius, feats[b2,idx,0:C]], b=b2/rep.
  * Replaces the fancy-index gathers of KNNGrouper.forward (common.py:99-120) and
- * group_with_centers_and_knn (common.py:126-187).  radius<=0 means None.  feats [B*rep,N,C]. */
-int psam_group_gather_f32(const float* xyz, const float* feats, const float* centers, const long long* knn_idx, int B,
-                          int rep, int N, int G, int K, int C, float radius, float* groups_out, cudaStream_t stream);
+ * group_with_centers_and_knn (common.py:126-187).  radius<=0 means None.  feats [B*rep,N,C].
+ * center_idx [B,G] (may be NULL) selects centralize_features=True (common.py:116-118, :181-185): C more channels
+ * feats[b2,idx] - feats[b2,center_idx[b,g]] are appended (groups_out row = 3 + 2C floats). */
+int psam_group_gather_f32(const float* xyz, const float* feats, const float* centers, const long long* knn_idx,
+                          const long long* center_idx, int B, int rep, int N, int G, int K, int C, float radius,
+                          float* groups_out, cudaStream_t stream);
+
+/* Voronoi tokenizer features: out[b2,n,:] = [(xyz[b,n]-c)/max(|xyz[b,n]-c|,1e-8), |xyz[b,n]-c|, feats[b2,n,0:C]] with
+ * c = centers[b, nn_idx[b,n]], b = b2/rep.  Replaces NNGrouper.forward / group_with_centers_and_nn
+ * (common.py:190-236).  out fp32 [B*rep,N,4+C] and / or the split-bf16 copy y_hi (row pitch `pitch` >= 4+C, zero
+ * padded) that feeds PatchEmbedNN.in_proj (pc_encoder.py:186) on the tensor cores. */
+int psam_voronoi_features_f32(const float* xyz, const float* centers, const long long* nn_idx, const float* feats, int B,
+                              int rep, int N, int G, int C, float* out, void* y_hi, long long y_plane, long long pitch,
+                              cudaStream_t stream);
+
+/* y[b, nn_idx[b,n], :] = max over the points of a Voronoi cell of x[b,n,:]; cells without a point are 0.
+ * Replaces y.scatter_reduce_(1, nn_idx, x, "amax", include_self=False) on a zero tensor (pc_encoder.py:189-193).
+ * x [B,N,D], y [B,G,D], D % 4 == 0. */
+int psam_scatter_amax_f32(const float* x, const long long* nn_idx, int B, int N, int G, int D, float* y,
+                          cudaStream_t stream);
 
 /* 3 nearest centres per point and inverse-squared-distance weights.
  * Replaces compute_interp_weights (common.py:238-255).  idx_out [B,N,3] int64, w_out [B,N,3]. */

@@ -132,13 +132,64 @@ def sampler_fixture(ref, out_dir):
     print("prompt sampler fixture written:", [tuple(pack[f"coords{i}"].shape) for i in range(len(preds))])
 
 
+VORONOI = dict(B=2, N=3000, G=96, hidden=64, out=96, seed=7)      # PatchEmbedNN(7, hidden, out, G)
+GROUPER_OPTS = dict(B=2, N=1500, G=40, K=24, radius=0.3, seed=8)   # KNNGrouper(use_fps=False, centralize_features=True)
+
+
+@torch.no_grad()
+def variant_fixture(ref, out_dir):
+    """Outputs of the reference's own NNGrouper / PatchEmbedNN (Voronoi tokenizer, common.py:190-236, pc_encoder.py:147-197) and
+    of KNNGrouper with use_fps=False / centralize_features=True (common.py:93-96, :116-118), exact-distance cdist."""
+    orig = torch.cdist
+    torch.cdist = lambda a, b, **kw: orig(a, b, compute_mode="donot_use_mm_for_euclid_dist")
+    try:
+        v = VORONOI
+        xyz, feats = synth.make_batch(v["B"], v["N"], v["seed"], "ball")
+        torch.manual_seed(4321)
+        oracle = torch_ref.PatchEmbedNN(7, v["hidden"], v["out"], v["G"]).eval()
+        model = ref["enc"].PatchEmbedNN(7, v["hidden"], v["out"], v["G"]).eval()
+        model.load_state_dict(oracle.state_dict(), strict=True)
+        patches = model(xyz, feats)
+        want = oracle(xyz, feats)
+        for k in ("features", "centers", "nn_idx", "embeddings"):
+            assert torch.allclose(patches[k].double(), want[k].double(), atol=1e-6), k
+        g = GROUPER_OPTS
+        xyz2, feats2 = synth.make_batch(g["B"], g["N"], g["seed"], "ball")
+        grp = ref["common"].KNNGrouper(g["G"], g["K"], radius=g["radius"], centralize_features=True)
+        out2 = grp(xyz2, feats2, use_fps=False)
+        np.savez_compressed(
+            os.path.join(out_dir, "variants.npz"),
+            voronoi_meta=np.array([v["B"], v["N"], v["G"], v["hidden"], v["out"], v["seed"]]),
+            voronoi_weights_checksum=state_checksum(model.state_dict()),
+            voronoi_xyz=xyz.numpy(), voronoi_feats=feats.numpy(), voronoi_features=patches["features"].numpy(),
+            voronoi_centers=patches["centers"].numpy(), voronoi_nn_idx=patches["nn_idx"].numpy().astype(np.int32),
+            voronoi_embeddings=patches["embeddings"].numpy(),
+            grouper_meta=np.array([g["B"], g["N"], g["G"], g["K"], g["seed"]]), grouper_radius=g["radius"],
+            grouper_xyz=xyz2.numpy(), grouper_feats=feats2.numpy(), grouper_features_sorted=_sorted_groups(out2).numpy(),
+            grouper_centers=out2["centers"].numpy(), grouper_fps_idx=out2["fps_idx"].numpy().astype(np.int32),
+        )
+        print("variant fixture written: voronoi embeddings", tuple(patches["embeddings"].shape), "grouper features",
+              tuple(out2["features"].shape))
+    finally:
+        torch.cdist = orig
+
+
+def _sorted_groups(out):
+    """Group features with the K members of every group ordered by key index (the reference's topk order is unspecified)."""
+    order = torch.argsort(out["knn_idx"], dim=-1)
+    return torch.gather(out["features"], 2, order.unsqueeze(-1).expand_as(out["features"]))
+
+
 @torch.no_grad()
 def main():
     torch.set_num_threads(8)
     ref = import_reference()
     out_dir = os.path.join(REPO, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--only-variants" in sys.argv:
+        return variant_fixture(ref, out_dir)
     sampler_fixture(ref, out_dir)
+    variant_fixture(ref, out_dir)
     if "--only-sampler" in sys.argv:
         return
     for name, B, N, G, K, encoder, P, kind, seed in CASES:

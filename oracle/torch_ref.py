@@ -186,6 +186,67 @@ class PatchEmbed(nn.Module):
         return patches
 
 
+class NNGrouper(nn.Module):
+    """pc_sam/model/common.py:190-212 (Voronoi grouping: every point joins its nearest FPS centre)."""
+
+    def __init__(self, num_groups: int):
+        super().__init__()
+        self.num_groups = num_groups
+
+    def forward(self, xyz, features):
+        with torch.no_grad():
+            fps_idx = sample_farthest_points(xyz.float(), self.num_groups)
+            centers = batch_index_select(xyz, fps_idx, dim=1)
+            _, nn_idx = knn_points(xyz, centers, 1)
+        nn_idx = nn_idx.squeeze(-1)
+        return dict(features=group_with_centers_and_nn(xyz, features, centers, nn_idx), centers=centers, nn_idx=nn_idx)
+
+
+def group_with_centers_and_nn(xyz, features, centers, nn_idx):
+    """pc_sam/model/common.py:214-236."""
+    nbr_xyz = xyz - batch_index_select(centers, nn_idx, dim=1)
+    dist = torch.linalg.norm(nbr_xyz, dim=-1, keepdim=True, ord=2)
+    nbr_xyz = nbr_xyz / torch.clamp(dist, min=1e-8)
+    return torch.cat([nbr_xyz, dist, features], dim=-1)
+
+
+class Block(nn.Module):
+    """pc_sam/model/pc_encoder.py:147-162."""
+
+    def __init__(self, in_channels, hidden_dim, out_channels):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(in_channels, hidden_dim), nn.GELU(), nn.LayerNorm(hidden_dim),
+                                 nn.Linear(hidden_dim, out_channels))
+        self.norm = nn.LayerNorm(out_channels)
+
+    def forward(self, x):
+        return x + self.mlp(self.norm(x))
+
+
+class PatchEmbedNN(nn.Module):
+    """pc_sam/model/pc_encoder.py:165-197."""
+
+    def __init__(self, in_channels, hidden_dim, out_channels, num_patches):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        hidden_dim = hidden_dim or out_channels
+        self.grouper = NNGrouper(num_patches)
+        self.in_proj = nn.Linear(in_channels, hidden_dim)
+        self.blocks1 = nn.Sequential(*[Block(hidden_dim, hidden_dim, hidden_dim) for _ in range(3)])
+        self.blocks2 = nn.Sequential(*[Block(hidden_dim, hidden_dim, hidden_dim) for _ in range(3)])
+        self.norm = nn.LayerNorm(hidden_dim)
+        self.out_proj = nn.Linear(hidden_dim, out_channels)
+
+    def forward(self, coords, features):
+        patches = self.grouper(coords, features)
+        nn_idx = patches["nn_idx"]
+        x = self.blocks1(self.in_proj(patches["features"]))
+        y = x.new_zeros(x.shape[0], self.grouper.num_groups, x.shape[-1])
+        y.scatter_reduce_(1, nn_idx.unsqueeze(-1).expand_as(x), x, "amax", include_self=False)
+        patches["embeddings"] = self.out_proj(self.norm(self.blocks2(y)))
+        return patches
+
+
 # --------------------------------------------------------------------------------------------
 # timm EVA / EVA02 blocks (restated; rope=None, no CLS/abs-pos on the Point-SAM path)
 # --------------------------------------------------------------------------------------------

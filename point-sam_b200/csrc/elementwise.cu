@@ -2,6 +2,7 @@
 // layer, group max-pool, softmax, positional encoding, small attention, upsampling, mask product).
 // Each kernel cites the reference op it replaces in include/psam_b200.h.
 #include <cstdlib>
+#include <math.h>
 #include "psam_common.cuh"
 #include "../../include/psam_b200.h"
 
@@ -269,7 +270,7 @@ swiglu_ln_kernel(const float* __restrict__ gx, long long ld, long long x_off, in
     for (int c = H + threadIdx.x; c < pitch; c += 256) store_split(yh, y_plane, row * ldy_s + c, 0.f);
 }
 
-// y = act(LN?(x W^T + b)); Cin <= 8; one warp per row, lane owns outputs lane, lane+32, ...
+// y = act(LN?(x W^T + b)); Cin <= 16; one warp per row, lane owns outputs lane, lane+32, ...
 template <int CPL>  // outputs per lane = Cout / 32
 __global__ void small_in_linear_kernel(const float* __restrict__ x, int rows, int Cin, const float* __restrict__ W,
                                        const float* __restrict__ b, const float* __restrict__ gamma,
@@ -284,9 +285,9 @@ __global__ void small_in_linear_kernel(const float* __restrict__ x, int rows, in
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
-        float xin[8];
+        float xin[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) xin[c] = c < Cin ? x[row * Cin + c] : 0.f;
+        for (int c = 0; c < 16; ++c) xin[c] = c < Cin ? x[row * Cin + c] : 0.f;
         float o[CPL];
         float s = 0.f;
 #pragma unroll
@@ -309,6 +310,68 @@ __global__ void small_in_linear_kernel(const float* __restrict__ x, int rows, in
 #pragma unroll
         for (int i = 0; i < CPL; ++i) store_split(yh, y_plane, row * ldy_s + lane + 32 * i, apply_act(o[i], act));
     }
+}
+
+// Voronoi tokenizer (NNGrouper.forward / group_with_centers_and_nn, pc_sam/model/common.py:190-236): every point is
+// described relative to its nearest centre: [ unit direction (3), distance (1), features (C) ].  Also writes the
+// split-bf16 copy (row pitch `pitch`, zero padded) that feeds in_proj on the tensor cores.
+__global__ void voronoi_features_kernel(const float* __restrict__ xyz, const float* __restrict__ centers,
+                                        const long long* __restrict__ nn_idx, const float* __restrict__ feats, int B2, int rep,
+                                        int N, int G, int C, float* __restrict__ out, __nv_bfloat16* __restrict__ yh,
+                                        long long y_plane, long long pitch) {
+    pdl_prologue();
+    const long long total = (long long)B2 * N;
+    const int CO = 4 + C;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
+        const int b2 = (int)(r / N), b = b2 / rep;
+        const long long n = r % N;
+        const float* p = xyz + ((size_t)b * N + n) * 3;
+        const float* c = centers + ((size_t)b * G + nn_idx[(size_t)b * N + n]) * 3;
+        const float dx = p[0] - c[0], dy = p[1] - c[1], dz = p[2] - c[2];
+        const float dist = sqrtf(dx * dx + dy * dy + dz * dz);  // torch.linalg.norm: sqrt of the plain sum of squares
+        const float inv = 1.0f / fmaxf(dist, 1e-8f);            // nbr_xyz / clamp(dist, min=1e-8)
+        float v[4] = {dx * inv, dy * inv, dz * inv, dist};
+        float* o = out ? out + (size_t)r * CO : nullptr;
+        const float* f = feats + (size_t)r * C;
+        for (int ch = 0; ch < CO; ++ch) {
+            const float x = ch < 4 ? v[ch] : f[ch - 4];
+            if (o) o[ch] = x;
+            if (yh) store_split(yh, y_plane, r * pitch + ch, x);
+        }
+        if (yh)
+            for (long long ch = CO; ch < pitch; ++ch) store_split(yh, y_plane, r * pitch + ch, 0.f);
+    }
+}
+
+__global__ void fill_f32_kernel(float* __restrict__ y, long long n, float v) {
+    pdl_prologue();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = v;
+}
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// y[b, nn_idx[b, n], :] = max over the points n of a cell (scatter_reduce_("amax", include_self=False) on a zero tensor,
+// pc_encoder.py:189-193): y is pre-filled with -inf, cells that receive no point are reset to the zero the reference keeps.
+__global__ void scatter_amax_kernel(const float* __restrict__ x, const long long* __restrict__ nn_idx, long long rows, int N, int G,
+                                    int D, float* __restrict__ y) {
+    pdl_prologue();
+    const long long total = rows * (D / 4);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / (D / 4);
+        const int c4 = (int)(i % (D / 4)) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + r * D + c4);
+        float* o = y + ((r / N) * G + nn_idx[r]) * (long long)D + c4;
+        atomic_max_float(o, v.x), atomic_max_float(o + 1, v.y), atomic_max_float(o + 2, v.z), atomic_max_float(o + 3, v.w);
+    }
+}
+
+__global__ void scatter_amax_finish_kernel(float* __restrict__ y, long long n) {
+    pdl_prologue();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        if (y[i] == __int_as_float(0xff800000)) y[i] = 0.f;
 }
 
 __global__ void group_max_kernel(const float* __restrict__ x, long long ldx, int groups, int K, int D, float* __restrict__ y,
@@ -942,7 +1005,7 @@ extern "C" int psam_swiglu_ln(const float* gx, long long ld, long long x_off, in
 extern "C" int psam_small_in_linear(const float* x, int rows, int Cin, const float* W, const float* b, const float* gamma,
                                     const float* beta, float eps, int use_ln, int act, int Cout, void* y_hi,
                                     long long y_plane, long long ldy_s, cudaStream_t stream) {
-    if (!x || !W || !y_hi || rows <= 0 || Cin <= 0 || Cin > 8 || Cout % 32 || Cout <= 0 || Cout > 512) return PSAM_ERR_ARG;
+    if (!x || !W || !y_hi || rows <= 0 || Cin <= 0 || Cin > 16 || Cout % 32 || Cout <= 0 || Cout > 512) return PSAM_ERR_ARG;
     if (use_ln && (!gamma || !beta)) return PSAM_ERR_ARG;
     const size_t smem = (size_t)(Cout * Cin + Cout) * sizeof(float);
     const int blocks = grid_for(rows, 8, 148 * 8);
@@ -1126,3 +1189,35 @@ extern "C" int psam_linear_f32(const psam_linear_args* a, cudaStream_t stream) {
 }
 
 extern "C" const char* psam_version(void) { return "psam_b200 0.1 (sm_100a)"; }
+
+extern "C" int psam_voronoi_features_f32(const float* xyz, const float* centers, const long long* nn_idx, const float* feats, int B,
+                                         int rep, int N, int G, int C, float* out, void* y_hi, long long y_plane, long long pitch,
+                                         cudaStream_t stream) {
+    using namespace psam;
+    if (!xyz || !centers || !nn_idx || !feats || (!out && !y_hi) || B <= 0 || rep <= 0 || N <= 0 || G <= 0 || C < 0) return PSAM_ERR_ARG;
+    if (y_hi && pitch < 4 + C) return PSAM_ERR_ARG;
+    const long long total = (long long)B * rep * N;
+    const int blocks = (int)min((long long)148 * 16, ceil_div_ll(total, 256));
+    PSAM_CUDA_TRY(psam::launch(voronoi_features_kernel, dim3(blocks), dim3(256), (size_t)0, stream, xyz, centers, nn_idx, feats, B * rep, rep, N, G,
+                               C, out, (__nv_bfloat16*)y_hi, y_plane, pitch));
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
+
+extern "C" int psam_scatter_amax_f32(const float* x, const long long* nn_idx, int B, int N, int G, int D, float* y, cudaStream_t stream) {
+    using namespace psam;
+    if (!x || !nn_idx || !y || B <= 0 || N <= 0 || G <= 0 || D <= 0 || (D & 3)) return PSAM_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return PSAM_ERR_ARG;
+    const long long n = (long long)B * G * D;
+    {
+        // -inf fill, scatter, reset of the empty cells
+        const int fb = (int)min((long long)148 * 8, ceil_div_ll(n, 256));
+        PSAM_CUDA_TRY(psam::launch(fill_f32_kernel, dim3(fb), dim3(256), (size_t)0, stream, y, n, -INFINITY));
+        const long long work = (long long)B * N * (D / 4);
+        const int sb = (int)min((long long)148 * 16, ceil_div_ll(work, 256));
+        PSAM_CUDA_TRY(psam::launch(scatter_amax_kernel, dim3(sb), dim3(256), (size_t)0, stream, x, nn_idx, (long long)B * N, N, G, D, y));
+        PSAM_CUDA_TRY(psam::launch(scatter_amax_finish_kernel, dim3(fb), dim3(256), (size_t)0, stream, y, n));
+    }
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}

@@ -439,13 +439,15 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ key, int Q
     }
 }
 
-// groups[b2, g, k, :] = [ (xyz[b, idx] - centers[b, g]) / radius , feats[b2, idx, 0:C] ]  (b = b2 / rep)
+// groups[b2, g, k, :] = [ (xyz[b, idx] - centers[b, g]) / radius , feats[b2, idx, 0:C] (, feats[b2, idx] - feats[b2, center_idx[b, g]]) ]
+// (b = b2 / rep; the third part only with center_idx: centralize_features=True, common.py:116-118 / :181-185)
 __global__ void group_gather_kernel(const float* __restrict__ xyz, const float* __restrict__ feats,
-                                    const float* __restrict__ centers, const long long* __restrict__ knn_idx, int B2,
+                                    const float* __restrict__ centers, const long long* __restrict__ knn_idx,
+                                    const long long* __restrict__ center_idx, int B2,
                                     int rep, int N, int G, int K, int C, float inv_radius, float* __restrict__ out) {
     pdl_prologue();
     const long long total = (long long)B2 * G * K;
-    const int CO = 3 + C;
+    const int CO = 3 + C + (center_idx ? C : 0);
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x) {
         const int b2 = (int)(r / ((long long)G * K));
         const int g = (int)((r / K) % G);
@@ -460,6 +462,10 @@ __global__ void group_gather_kernel(const float* __restrict__ xyz, const float* 
         o[2] = (p[2] - c[2]) * inv_radius;
         const float* f = feats + ((size_t)b2 * N + j) * C;
         for (int ch = 0; ch < C; ++ch) o[3 + ch] = f[ch];
+        if (center_idx) {
+            const float* fc = feats + ((size_t)b2 * N + center_idx[(size_t)b * G + g]) * C;
+            for (int ch = 0; ch < C; ++ch) o[3 + C + ch] = f[ch] - fc[ch];
+        }
     }
 }
 
@@ -777,13 +783,13 @@ extern "C" int psam_knn_f32(const float* query, const float* key, int B, int Q, 
 }
 
 extern "C" int psam_group_gather_f32(const float* xyz, const float* feats, const float* centers,
-                                     const long long* knn_idx, int B, int rep, int N, int G, int K, int C, float radius,
-                                     float* groups_out, cudaStream_t stream) {
+                                     const long long* knn_idx, const long long* center_idx, int B, int rep, int N, int G, int K,
+                                     int C, float radius, float* groups_out, cudaStream_t stream) {
     using namespace psam;
     if (!xyz || !feats || !centers || !knn_idx || !groups_out || B <= 0 || rep <= 0 || C < 0) return PSAM_ERR_ARG;
     const long long total = (long long)B * rep * G * K;
     const int blocks = (int)min((long long)148 * 16, ceil_div_ll(total, 256));
-    PSAM_CUDA_TRY(psam::launch(group_gather_kernel, dim3(blocks), dim3(256), (size_t)(0), stream, xyz, feats, centers, knn_idx, B * rep, rep, N, G, K, C,
+    PSAM_CUDA_TRY(psam::launch(group_gather_kernel, dim3(blocks), dim3(256), (size_t)(0), stream, xyz, feats, centers, knn_idx, center_idx, B * rep, rep, N, G, K, C,
                                                     radius > 0.f ? 1.0f / radius : 1.0f, groups_out));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;

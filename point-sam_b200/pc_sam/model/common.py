@@ -65,10 +65,28 @@ def repeat_interleave(x: torch.Tensor, repeats: int, dim: int):
 
 
 def group_with_centers_and_knn(xyz, features, centers, knn_idx, radius=None, centralize_features=False, center_idx=None):
-    if centralize_features:
-        raise NotImplementedError("centralize_features=True is not used by the released configs")
+    """common.py:126-187; centralize_features appends features[knn] - features[center_idx] (:181-185)."""
+    if centralize_features and center_idx is None:
+        raise RuntimeError("center_idx is required when centralize_features=True")
     return ops.group_gather(xyz.float().contiguous(), features.float().contiguous(), centers.contiguous(),
-                            knn_idx.contiguous(), radius)
+                            knn_idx.contiguous(), radius, center_idx=center_idx.contiguous() if centralize_features else None)
+
+
+def group_with_centers_and_nn(xyz, features, centers, nn_idx):
+    """Voronoi grouping (common.py:214-236): [unit direction to the nearest centre, distance, features] per point."""
+    return ops.voronoi_features(xyz.float().contiguous(), centers.float().contiguous(), nn_idx.contiguous(),
+                                features.float().contiguous())
+
+
+class NNGrouper(nn.Module):
+    """Group points by their nearest FPS centre (common.py:190-212)."""
+
+    def __init__(self, num_groups: int):
+        super().__init__()
+        self.num_groups = num_groups
+
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor):
+        return engine.run_nn_grouper(self, xyz, features)
 
 
 class KNNGrouper(nn.Module):

@@ -6,7 +6,7 @@ from torch import nn
 
 from psam_b200 import engine
 
-from .common import KNNGrouper, PatchEncoder
+from .common import KNNGrouper, NNGrouper, PatchEncoder
 
 
 class PatchEmbed(nn.Module):
@@ -22,6 +22,42 @@ class PatchEmbed(nn.Module):
         patches = self.grouper(coords, features)
         patches["embeddings"] = self.patch_encoder(patches["features"])
         return patches
+
+
+class Block(nn.Module):
+    """Residual MLP block of the Voronoi patch embedding (pc_encoder.py:147-162); parameters only - PatchEmbedNN runs it."""
+
+    def __init__(self, in_channels, hidden_dim, out_channels):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(in_channels, hidden_dim), nn.GELU(), nn.LayerNorm(hidden_dim),
+                                 nn.Linear(hidden_dim, out_channels))
+        self.norm = nn.LayerNorm(out_channels)
+
+    def forward(self, x):
+        shape = x.shape
+        y = x.float().reshape(-1, shape[-1]).clone()
+        engine._run_res_blocks([engine._PackedResBlock(self)], y)
+        return y.view(shape)
+
+
+class PatchEmbedNN(nn.Module):
+    """Voronoi tokenizer (pc_encoder.py:165-197): NNGrouper -> in_proj -> 3 Blocks per point -> maximum per cell ->
+    3 Blocks per cell -> LayerNorm -> out_proj."""
+
+    def __init__(self, in_channels, hidden_dim, out_channels, num_patches) -> None:
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        hidden_dim = hidden_dim or out_channels
+        self.grouper = NNGrouper(num_patches)
+        self.in_proj = nn.Linear(in_channels, hidden_dim)
+        self.blocks1 = nn.Sequential(*[Block(hidden_dim, hidden_dim, hidden_dim) for _ in range(3)])
+        self.blocks2 = nn.Sequential(*[Block(hidden_dim, hidden_dim, hidden_dim) for _ in range(3)])
+        self.norm = nn.LayerNorm(hidden_dim)
+        self.out_proj = nn.Linear(hidden_dim, out_channels)
+
+    def forward(self, coords: torch.Tensor, features: torch.Tensor):
+        return engine.run_patch_embed_nn(self, coords, features)
 
 
 class PointCloudEncoder(nn.Module):

@@ -100,12 +100,14 @@ class PointCloudSAM(nn.Module):
 
         return PipelinedPredictor(self, batch_size, num_points, num_prompts, depth, multimask_output, use_graph)
 
-    def make_iterative_predictor(self, batch_size: int, num_masks: int, num_points: int, use_graph: bool = True):
+    def make_iterative_predictor(self, batch_size: int, num_masks: int, num_points: int, use_graph: bool = True,
+                                 throughput_tiles: bool = False):
         """forward(is_eval=True) - encoder, then `prompt_iters` rounds of (GT prompt sampling, prompt / mask encoders,
-        decoder, best-mask feedback) - captured as ONE CUDA graph with no host synchronisation inside."""
+        decoder, best-mask feedback) - captured as ONE CUDA graph with no host synchronisation inside.
+        throughput_tiles: capture with the SM-time-optimal GEMM tile policy (several predictors in flight on one GPU)."""
         from psam_b200.predictor import IterativeGraphPredictor
 
-        return IterativeGraphPredictor(self, batch_size, num_masks, num_points, use_graph)
+        return IterativeGraphPredictor(self, batch_size, num_masks, num_points, use_graph, throughput_tiles=throughput_tiles)
 
     # ------------------------------------------------------------------------------------------
     def predict_iterative(self, coords, features, prompt_coords_seq: List[torch.Tensor],

@@ -128,20 +128,94 @@ def run_patch_encoder(m, patches: torch.Tensor, want_split: bool = False):
 # KNNGrouper, pc_sam/model/common.py:59-123
 # ------------------------------------------------------------------------------------------------
 def run_knn_grouper(g, xyz, features, use_fps=True):
-    if not use_fps:
-        raise NotImplementedError("use_fps=False is only used by the hierarchical variant (out of scope)")
     xyz32 = xyz.float().contiguous()
     feats = features.float().contiguous()
     B, N, _ = xyz32.shape
     if N < g.num_groups:
         raise RuntimeError("sample_farthest_points: number of points must be >= num_samples")
-    fps_idx, centers = ops.fps(xyz32, g.num_groups)
+    if use_fps:
+        fps_idx, centers = ops.fps(xyz32, g.num_groups)
+    else:  # `xyz` is already FPS-ordered: the first num_groups points are the centres (common.py:93-96)
+        fps_idx = torch.arange(g.num_groups, device=xyz.device).expand(B, -1).contiguous()
+        centers = xyz32[:, : g.num_groups].contiguous()
     knn_idx, _ = ops.knn(centers, xyz32, g.group_size)
-    src_feats = feats
-    if g.centralize_features:
-        raise NotImplementedError("centralize_features=True is not used by the released configs")
-    groups = ops.group_gather(xyz32, src_feats, centers, knn_idx, g.radius)
+    groups = ops.group_gather(xyz32, feats, centers, knn_idx, g.radius,
+                              center_idx=fps_idx if g.centralize_features else None)  # common.py:116-118
     return dict(features=groups, centers=centers, knn_idx=knn_idx, fps_idx=fps_idx)
+
+
+# ------------------------------------------------------------------------------------------------
+# Voronoi tokenizer: NNGrouper (common.py:190-212), PatchEmbedNN + Block (pc_encoder.py:147-197)
+# ------------------------------------------------------------------------------------------------
+def run_nn_grouper(g, xyz, features, want_split: bool = False):
+    xyz32 = xyz.float().contiguous()
+    feats = features.float().contiguous()
+    if xyz32.shape[1] < g.num_groups:
+        raise RuntimeError("sample_farthest_points: number of points must be >= num_samples")
+    _, centers = ops.fps(xyz32, g.num_groups)
+    nn_idx = ops.nn_index(xyz32, centers)  # knn_points(xyz, centers, 1): nearest centre of every point
+    out = ops.voronoi_features(xyz32, centers, nn_idx, feats, want_split=want_split)
+    gf, sp = out if want_split else (out, None)
+    d = dict(features=gf, centers=centers, nn_idx=nn_idx)
+    if want_split:
+        d["_features_split"] = sp
+    return d
+
+
+class _PackedResBlock:
+    """Block (pc_encoder.py:147-162): x + Linear(LayerNorm(GELU(Linear(LayerNorm(x)))))."""
+
+    def __init__(self, blk):
+        lin1, ln_mid, lin2 = blk.mlp[0], blk.mlp[2], blk.mlp[3]
+        self.g0, self.b0, self.eps0 = _f32(blk.norm.weight), _f32(blk.norm.bias), blk.norm.eps
+        self.w1, self.bb1 = ops.pack_weight(lin1.weight), _f32(lin1.bias)
+        self.g1, self.b1, self.eps1 = _f32(ln_mid.weight), _f32(ln_mid.bias), ln_mid.eps
+        self.w2, self.bb2 = ops.pack_weight(lin2.weight), _f32(lin2.bias)
+        self.hid = lin1.out_features
+
+
+class _PackedPatchEmbedNN:
+    def __init__(self, m):
+        self.hid = m.in_proj.out_features
+        self.win, self.bin = ops.pack_weight(m.in_proj.weight), _f32(m.in_proj.bias)
+        self.blocks1 = [_PackedResBlock(b) for b in m.blocks1]
+        self.blocks2 = [_PackedResBlock(b) for b in m.blocks2]
+        self.g, self.b, self.eps = _f32(m.norm.weight), _f32(m.norm.bias), m.norm.eps
+        self.wout, self.bout = ops.pack_weight(m.out_proj.weight), _f32(m.out_proj.bias)
+
+
+def _run_res_blocks(blocks, x: torch.Tensor):
+    """x fp32 [rows, D], updated in place."""
+    rows, D = x.shape
+    dev = x.device
+    for pb in blocks:
+        xn = Split(rows, D, dev)
+        ops.layernorm(x, pb.g0, pb.b0, pb.eps0, out_split=xn)
+        u = torch.empty((rows, pb.hid), dtype=torch.float32, device=dev)
+        ops.gemm(xn, pb.w1, bias=pb.bb1, out_f32=u, act=ACT_GELU, passes=PASSES)
+        un = Split(rows, pb.hid, dev)
+        ops.layernorm(u, pb.g1, pb.b1, pb.eps1, out_split=un)
+        ops.gemm(un, pb.w2, bias=pb.bb2, out_f32=x, resid=x, passes=PASSES)
+
+
+def run_patch_embed_nn(m, coords, features):
+    """PatchEmbedNN.forward (pc_encoder.py:181-197): per-point residual MLPs, maximum per Voronoi cell, per-cell MLPs."""
+    pk = _cached(m, _PackedPatchEmbedNN)
+    patches = run_nn_grouper(m.grouper, coords, features, want_split=True)
+    fs = patches.pop("_features_split")
+    B, N, _ = patches["features"].shape
+    G, dev = m.grouper.num_groups, coords.device
+    x = torch.empty((B * N, pk.hid), dtype=torch.float32, device=dev)
+    ops.gemm(fs, pk.win, bias=pk.bin, out_f32=x, passes=PASSES)
+    _run_res_blocks(pk.blocks1, x)
+    y = ops.scatter_amax(x.view(B, N, pk.hid), patches["nn_idx"], G).view(B * G, pk.hid)
+    _run_res_blocks(pk.blocks2, y)
+    yn = Split(B * G, pk.hid, dev)
+    ops.layernorm(y, pk.g, pk.b, pk.eps, out_split=yn)
+    emb = torch.empty((B, G, m.out_channels), dtype=torch.float32, device=dev)
+    ops.gemm(yn, pk.wout, bias=pk.bout, out_f32=emb.view(B * G, -1), passes=PASSES)
+    patches["embeddings"] = emb
+    return patches
 
 
 # ------------------------------------------------------------------------------------------------

@@ -72,14 +72,48 @@ def knn(query: torch.Tensor, key: torch.Tensor, k: int, want_d2: bool = False):
     return idx, d2
 
 
-def group_gather(xyz, feats, centers, knn_idx, radius=None):
+def group_gather(xyz, feats, centers, knn_idx, radius=None, center_idx=None):
+    """center_idx [B,G] int64: centralize_features=True (C more channels feats[idx] - feats[center])."""
     B, N, _ = xyz.shape
     B2, _, C = feats.shape
     _, G, K = knn_idx.shape
-    out = torch.empty((B2, G, K, 3 + C), dtype=torch.float32, device=xyz.device)
-    nv.check(nv.lib().psam_group_gather_f32(nv.ptr(xyz), nv.ptr(feats), nv.ptr(centers), nv.ptr(knn_idx), B, B2 // B, N, G, K, C,
-                                            float(radius) if radius else 0.0, nv.ptr(out), nv.stream()), "group_gather")
+    out = torch.empty((B2, G, K, 3 + C + (C if center_idx is not None else 0)), dtype=torch.float32, device=xyz.device)
+    nv.check(nv.lib().psam_group_gather_f32(nv.ptr(xyz), nv.ptr(feats), nv.ptr(centers), nv.ptr(knn_idx), nv.ptr(center_idx), B, B2 // B,
+                                            N, G, K, C, float(radius) if radius else 0.0, nv.ptr(out), nv.stream()), "group_gather")
     return out
+
+
+def nn_index(query, key):
+    """Nearest key of every query point, one cloud at a time (first index on ties): idx [B,Nq] int64."""
+    B, Nq, _ = query.shape
+    Nk = key.shape[1]
+    idx = torch.empty((B, Nq), dtype=torch.int64, device=query.device)
+    dist = torch.empty((B, Nq), dtype=torch.float32, device=query.device)
+    for b in range(B):
+        nv.check(nv.lib().psam_nn_distance_f32(nv.ptr(query[b]), nv.ptr(key[b]), Nq, Nk, nv.ptr(dist[b]), nv.ptr(idx[b]), nv.stream()),
+                 "nn_distance")
+    return idx
+
+
+def voronoi_features(xyz, centers, nn_idx, feats, want_split: bool = False):
+    """[unit direction to the nearest centre, distance, features] per point: fp32 [B2,N,4+C] (+ split copy, pitch 64)."""
+    B, N, _ = xyz.shape
+    B2, _, C = feats.shape
+    out = torch.empty((B2, N, 4 + C), dtype=torch.float32, device=xyz.device)
+    sp = Split(B2 * N, 4 + C, xyz.device) if want_split else None
+    nv.check(nv.lib().psam_voronoi_features_f32(nv.ptr(xyz), nv.ptr(centers), nv.ptr(nn_idx), nv.ptr(feats), B, B2 // B, N,
+                                                centers.shape[1], C, nv.ptr(out), sp.ptr() if sp is not None else None,
+                                                sp.plane if sp is not None else 0, sp.pitch if sp is not None else 0, nv.stream()),
+             "voronoi_features")
+    return (out, sp) if want_split else out
+
+
+def scatter_amax(x, nn_idx, G: int):
+    """x [B,N,D], nn_idx [B,N] -> [B,G,D] maximum per Voronoi cell (empty cells 0)."""
+    B, N, D = x.shape
+    y = torch.empty((B, G, D), dtype=torch.float32, device=x.device)
+    nv.check(nv.lib().psam_scatter_amax_f32(nv.ptr(x), nv.ptr(nn_idx), B, N, G, D, nv.ptr(y), nv.stream()), "scatter_amax")
+    return y
 
 
 def knn3_interp(xyz, centers):

@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import torch
 
-from . import engine, native as nv
+from . import engine, native as nv, ops
 
 
 class GraphPredictor:
@@ -114,9 +114,10 @@ class IterativeGraphPredictor:
     feedback.  The reference synchronises with the host several times per (cloud, mask, iteration); here the only host
     interaction is one flag read after the replay.  Returns the same list of per-iteration dicts as ``forward``."""
 
-    def __init__(self, model, B: int, M: int, N: int, use_graph: bool = True, device=None):
+    def __init__(self, model, B: int, M: int, N: int, use_graph: bool = True, device=None, throughput_tiles: bool = False):
         self.model = model
         self.dev = device or next(model.parameters()).device
+        self.throughput_tiles = throughput_tiles
         d = self.dev
         self.xyz = torch.zeros((B, N, 3), dtype=torch.float32, device=d)
         self.feats = torch.zeros((B, N, 3), dtype=torch.float32, device=d)
@@ -141,18 +142,24 @@ class IterativeGraphPredictor:
         self.gt.copy_(gt, non_blocking=True)
 
     def warmup(self, xyz, feats, gt):
-        with torch.no_grad(), torch.cuda.stream(self.stream):
-            self._load(xyz, feats, gt)
-            for _ in range(2):
-                n0 = nv.LAUNCHES[0]
-                self.outputs = self._run()  # eager: raises like the reference on bad inputs
-                self.launches_per_step = nv.LAUNCHES[0] - n0
+        prev = ops.GEMM_TILE_HINT
+        if self.throughput_tiles:
+            ops.GEMM_TILE_HINT = 1  # baked into the captured graph
+        try:
+            with torch.no_grad(), torch.cuda.stream(self.stream):
+                self._load(xyz, feats, gt)
+                for _ in range(2):
+                    n0 = nv.LAUNCHES[0]
+                    self.outputs = self._run()  # eager: raises like the reference on bad inputs
+                    self.launches_per_step = nv.LAUNCHES[0] - n0
+                self.stream.synchronize()
+                if self.use_graph:
+                    self.graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph, stream=self.stream):
+                        self.outputs = self._run()
             self.stream.synchronize()
-            if self.use_graph:
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph, stream=self.stream):
-                    self.outputs = self._run()
-        self.stream.synchronize()
+        finally:
+            ops.GEMM_TILE_HINT = prev
 
     def __call__(self, xyz, feats, gt, check: bool = True):
         caller = torch.cuda.current_stream(self.dev)

@@ -485,3 +485,45 @@ def test_config5_full_size_vs_fp32_oracle_on_gpu():
     """BASELINE config[4] model at full size: EVA-giant (40 blocks, 16 heads x 88, fused qkv with q/v bias, GELU MLP 6144),
     N=32768, group_number=512, group_size=64."""
     _full_size_parity("eva_giant_patch14_560", 512, 64, 32768, "ball", 43, False)
+
+
+@pytest.mark.gpu
+def test_voronoi_tokenizer_and_grouper_options_vs_reference_fixture(golden_dir):
+    """NNGrouper / PatchEmbedNN (Voronoi tokenizer: nearest-centre assignment, per-point residual MLPs on the tensor cores,
+    maximum per cell, per-cell MLPs) and KNNGrouper(use_fps=False, centralize_features=True) against outputs of the
+    reference's own modules (tests/golden/variants.npz)."""
+    from oracle import torch_ref
+    from oracle.make_golden import GROUPER_OPTS, VORONOI, state_checksum
+    from pc_sam.model.common import KNNGrouper, NNGrouper, group_with_centers_and_nn
+    from pc_sam.model.pc_encoder import PatchEmbedNN
+
+    z = np.load(os.path.join(golden_dir, "variants.npz"))
+    d = torch.device("cuda:0")
+    v = VORONOI
+    torch.manual_seed(4321)
+    oracle = torch_ref.PatchEmbedNN(7, v["hidden"], v["out"], v["G"]).eval()
+    assert state_checksum(oracle.state_dict()) == str(z["voronoi_weights_checksum"])
+    m = PatchEmbedNN(7, v["hidden"], v["out"], v["G"])
+    m.load_state_dict(oracle.state_dict(), strict=True)
+    m = m.to(d).eval()
+    xyz, feats = torch.from_numpy(z["voronoi_xyz"]).to(d), torch.from_numpy(z["voronoi_feats"]).to(d)
+    with torch.no_grad():
+        out = m(xyz, feats)
+        grp = NNGrouper(v["G"])(xyz, feats)
+        again = group_with_centers_and_nn(xyz, feats, out["centers"], out["nn_idx"])
+    assert np.array_equal(out["nn_idx"].cpu().numpy(), z["voronoi_nn_idx"])
+    np.testing.assert_allclose(out["centers"].cpu().numpy(), z["voronoi_centers"], atol=0)
+    np.testing.assert_allclose(out["features"].cpu().numpy(), z["voronoi_features"], atol=2e-6)
+    np.testing.assert_allclose(grp["features"].cpu().numpy(), z["voronoi_features"], atol=2e-6)
+    np.testing.assert_allclose(again.cpu().numpy(), z["voronoi_features"], atol=2e-6)
+    np.testing.assert_allclose(out["embeddings"].cpu().numpy(), z["voronoi_embeddings"], atol=2e-4, rtol=1e-4)
+    # KNNGrouper on FPS-ordered input with centralised features
+    g = GROUPER_OPTS
+    k = KNNGrouper(g["G"], g["K"], radius=g["radius"], centralize_features=True)
+    x2, f2 = torch.from_numpy(z["grouper_xyz"]).to(d), torch.from_numpy(z["grouper_feats"]).to(d)
+    with torch.no_grad():
+        o2 = k(x2, f2, use_fps=False)
+    assert np.array_equal(o2["fps_idx"].cpu().numpy(), z["grouper_fps_idx"])
+    order = torch.argsort(o2["knn_idx"], dim=-1)
+    got = torch.gather(o2["features"], 2, order.unsqueeze(-1).expand_as(o2["features"]))
+    np.testing.assert_allclose(got.cpu().numpy(), z["grouper_features_sorted"], atol=2e-6)
