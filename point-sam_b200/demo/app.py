@@ -102,7 +102,15 @@ class SegmentSession:
         return {"status": "saved"}
 
 
-def make_handler(session: SegmentSession, static_dir: str, model_dir: str):
+def make_handler(session: SegmentSession, static_dir: str, model_dir: str, pointcloud: str = None):
+    """pointcloud: the file every /pointcloud/<anything> request serves (the reference always loads args.pointcloud,
+    demo/app.py:91-126); None serves the requested basename from `model_dir`."""
+    import threading
+    from urllib.parse import urlparse
+
+    lock = threading.Lock()  # one model, one mutable session: requests are serialised like the reference's Flask dev server
+    static_root = os.path.realpath(static_dir)
+
     class Handler(BaseHTTPRequestHandler):
         def _json(self, obj, code=200):
             body = json.dumps(obj).encode()
@@ -113,11 +121,14 @@ def make_handler(session: SegmentSession, static_dir: str, model_dir: str):
             self.wfile.write(body)
 
         def do_GET(self):
-            if self.path.startswith("/pointcloud/"):
-                return self._json(session.pointcloud(os.path.join(model_dir, os.path.basename(self.path))))
-            rel = "index.html" if self.path == "/" else self.path.lstrip("/").replace("static/", "", 1)
-            p = os.path.normpath(os.path.join(static_dir, rel))
-            if not p.startswith(os.path.normpath(static_dir)) or not os.path.isfile(p):
+            path = urlparse(self.path).path
+            if path.startswith("/pointcloud/"):
+                name = pointcloud if pointcloud else os.path.basename(path)
+                with lock:
+                    return self._json(session.pointcloud(name if os.path.isabs(name) else os.path.join(model_dir, name)))
+            rel = "index.html" if path == "/" else path.lstrip("/").replace("static/", "", 1)
+            p = os.path.realpath(os.path.join(static_root, rel))
+            if os.path.commonpath([p, static_root]) != static_root or not os.path.isfile(p):
                 return self._json({"error": "not found"}, 404)
             with open(p, "rb") as f:
                 body = f.read()
@@ -131,11 +142,13 @@ def make_handler(session: SegmentSession, static_dir: str, model_dir: str):
             req = json.loads(self.rfile.read(n) or b"{}")
             routes = {"/segment": lambda: session.segment(req), "/sampled_pointcloud": lambda: session.sampled_pointcloud(req),
                       "/clear": session.clear, "/next": session.next, "/save": session.save}
-            fn = routes.get(self.path)
+            fn = routes.get(urlparse(self.path).path)
             if fn is None:
                 return self._json({"error": "not found"}, 404)
             try:
-                self._json(fn())
+                with lock:
+                    out = fn()
+                self._json(out)
             except (ValueError, RuntimeError) as e:
                 self._json({"error": str(e)}, 400)
 
@@ -161,7 +174,7 @@ def main(argv=None):
         load_model(model, args.ckpt_path)
     model.eval().cuda()
     session = SegmentSession(model)
-    srv = ThreadingHTTPServer((args.host, args.port), make_handler(session, args.static, os.path.join(args.static, "models")))
+    srv = ThreadingHTTPServer((args.host, args.port), make_handler(session, args.static, os.path.join(args.static, "models"), args.pointcloud))
     srv.serve_forever()
 
 

@@ -57,24 +57,43 @@ def _merge(dst: Dict, src: Dict) -> Dict:
     return dst
 
 
+def _load_group_file(directory: str, name: str) -> Dict:
+    """One YAML file with its own (group-level) defaults list resolved inside its directory, e.g.
+    configs/model/enc_with_radius.yaml: ``defaults: [default]`` then its own keys on top."""
+    with open(os.path.join(directory, name.lstrip("/") + ".yaml")) as f:
+        node = _load(f) or {}
+    out: Dict = {}
+    for d in node.pop("defaults", []) if isinstance(node, dict) else []:
+        if d == "_self_":
+            continue
+        if isinstance(d, str):
+            _merge(out, _load_group_file(directory, d))
+        else:
+            (group, option), = d.items()
+            sub = os.path.join(directory, group.partition("@")[0])
+            if os.path.exists(os.path.join(sub, str(option) + ".yaml")):
+                out[group.partition("@")[2] or group.partition("@")[0]] = _load_group_file(sub, str(option))
+    return _merge(out, node)
+
+
 def compose(config_dir: str, config_name: str, overrides=()) -> Dict:
     """``hydra.compose`` for the subset the reference uses: the defaults list (``group: option`` and
     ``group@dest: option``), ``_self_`` ordering, and ``a.b.c=value`` overrides.  ``${...}`` interpolations are left as
     text (only logging paths use them)."""
-    with open(os.path.join(config_dir, config_name + ".yaml")) as f:
-        root = _load(f) or {}
+    root = _load_group_file(config_dir, config_name)
     defaults = root.pop("defaults", [])
     cfg: Dict = {}
     for d in defaults:
         if d == "_self_":
             continue
+        if isinstance(d, str):  # `- other` : another file of the same directory merged at the root
+            _merge(cfg, _load_group_file(config_dir, d))
+            continue
         (group, option), = d.items()
         group, _, dest = group.partition("@")
-        p = os.path.join(config_dir, group, str(option) + ".yaml")
-        if not os.path.exists(p):
+        if not os.path.exists(os.path.join(config_dir, group, str(option) + ".yaml")):
             continue  # dataset/loss groups are not needed for inference
-        with open(p) as f:
-            cfg[dest or group] = _load(f) or {}
+        cfg[dest or group] = _load_group_file(os.path.join(config_dir, group), str(option))
     _merge(cfg, root)
     for ov in overrides:
         key, _, val = ov.partition("=")

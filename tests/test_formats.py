@@ -285,3 +285,52 @@ def test_forward_in_training_mode_is_refused():
     m = build_point_sam("eva02_test_tiny", 8, 4).train()
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 16, 3), torch.zeros(1, 16, 3), torch.zeros(1, 1, 16, dtype=torch.bool))
+
+
+def test_compose_resolves_group_level_and_string_defaults(tmp_path):
+    """configs/model/enc_with_radius.yaml style: a group file with its own `defaults: [default]` list (advisor finding)."""
+    from pc_sam.utils.config import compose
+
+    (tmp_path / "model").mkdir()
+    (tmp_path / "model" / "default.yaml").write_text("_target_: a.B\npc_encoder:\n  patch_embed:\n    num_patches: 1024\n    radius: null\n")
+    (tmp_path / "model" / "with_radius.yaml").write_text("defaults:\n  - default\n\npc_encoder:\n  patch_embed:\n    radius: 0.1\n")
+    (tmp_path / "top.yaml").write_text("defaults:\n  - model: with_radius\n  - _self_\nlr: 3e-4\n")
+    cfg = compose(str(tmp_path), "top")
+    assert cfg["model"]["_target_"] == "a.B"
+    assert cfg["model"]["pc_encoder"]["patch_embed"] == {"num_patches": 1024, "radius": 0.1}
+    assert cfg["lr"] == 3e-4
+
+
+def test_demo_static_guard_and_fixed_pointcloud(tmp_path):
+    """A sibling directory sharing the static directory's prefix is not served; query strings are ignored; the configured
+    point cloud is served whatever name the URL carries (demo/app.py:91-126 always loads args.pointcloud)."""
+    import io
+
+    from demo.app import make_handler
+
+    static = tmp_path / "static"
+    static.mkdir()
+    (static / "index.html").write_text("ok")
+    sib = tmp_path / "static_x"
+    sib.mkdir()
+    (sib / "secret.txt").write_text("no")
+
+    class FakeSession:
+        def pointcloud(self, path):
+            return {"path": path}
+
+    H = make_handler(FakeSession(), str(static), str(static / "models"), "scene.ply")
+
+    def get(path):
+        h = H.__new__(H)
+        h.path, h.wfile, h.headers = path, io.BytesIO(), {}
+        h.send_response = lambda code: setattr(h, "code", code)
+        h.send_header = lambda *a: None
+        h.end_headers = lambda: None
+        h.do_GET()
+        return h.code, h.wfile.getvalue()
+
+    assert get("/?v=3") == (200, b"ok")
+    assert get("/../static_x/secret.txt")[0] == 404
+    code, body = get("/pointcloud/whatever.ply?x=1")
+    assert code == 200 and body.decode().endswith('models/scene.ply"}')
