@@ -44,6 +44,7 @@ CONFIGS = {
     "c1": ("eva02_base_patch14_448", 4096, 128, 32, 1, 1, "ball"),
     "c2": ("eva02_large_patch14_448", 32768, 512, 64, 1, 1, "ball"),
     "c2b4": ("eva02_large_patch14_448", 32768, 512, 64, 4, 1, "ball"),
+    "c2b8": ("eva02_large_patch14_448", 32768, 512, 64, 8, 1, "ball"),
     "c4": ("eva02_large_patch14_448", 131072, 2048, 256, 1, 1, "kitti"),
     "c5": ("eva_giant_patch14_560", 32768, 512, 64, 1, 1, "ball"),
     "tiny": ("eva02_test_tiny", 2048, 64, 16, 1, 1, "ball"),
