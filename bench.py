@@ -290,7 +290,7 @@ def only_regime(pp, keep, reps: int):
     once more through OnlyLib into the lane's own graph memory pool (so the kernels run on the buffers the full graphs
     populate), then all `depth` reduced graphs are replayed concurrently `reps` times.
     Returns (elapsed ms per cloud of machine time, launches per cloud, algorithmic GEMM flops per cloud)."""
-    from psam_b200 import native as nv, ops
+    from psam_b200 import engine, native as nv, ops
 
     real = nv.lib()
     graphs, flops, launches = [], 0.0, 0
@@ -300,7 +300,7 @@ def only_regime(pp, keep, reps: int):
             proxy = OnlyLib(real, keep)
             nv._lib = proxy
             g = torch.cuda.CUDAGraph()
-            with torch.no_grad(), torch.cuda.graph(g, pool=lane.graph.pool(), stream=lane.stream):
+            with torch.no_grad(), torch.cuda.graph(g, pool=lane.graph.pool(), stream=lane.stream), engine.block_ln_fold(pp.ln_fold):
                 lane._run()
             nv._lib = real
             graphs.append(g)
@@ -588,7 +588,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3", "data": "synthetic", "config": workload_config(args, args.config),
-            "run": {"clouds_per_step": cps * bpg, "clouds_in_flight": pp.depth, "cuda_graph": pred.graph is not None,
+            "run": {"clouds_per_step": cps * bpg, "clouds_in_flight": pp.depth, "cuda_graph": pred.graph is not None, "layernorm_free_blocks": pp.ln_fold,
                     "numerics": "split-bf16 x3 tensor-core contractions (fp32-parity mode), fp32 everywhere else",
                     "single_stream_ms_per_cloud": ms_single, "ms_per_cloud": ms_per_cloud,
                     "timed_region_s": ms_dev / 1e3},
@@ -609,7 +609,7 @@ def main():
 
     # ---- roofline of the dominant kernel (rank 0) ---------------------------------------------------
     if rank == 0 and not args.no_roofline and pred.graph is not None:
-        from psam_b200 import ops
+        from psam_b200 import engine, ops
 
         pk, pk_src = peaks()
         peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
@@ -631,7 +631,7 @@ def main():
                             with torch.cuda.stream(lane.stream):
                                 for _ in range(10):
                                     lane.graph.replay()
-                        with torch.cuda.stream(stream):
+                        with torch.cuda.stream(stream), engine.block_ln_fold(pp.ln_fold):
                             pred._load(*devin[rep % n_rot])
                             if busy_lanes == 0:
                                 torch.cuda._sleep(int(25e-3 * 1.9e9))  # let the host run ahead of the device

@@ -30,7 +30,33 @@ FUSED_MASK_DOT = os.environ.get("PSAM_FUSED_MASK_DOT", "1") != "0"
 DECODER_TC = os.environ.get("PSAM_DECODER_TC", "1") != "0"
 # norm1 / norm2 / fc_norm folded into the qkv / fc1 / out_proj GEMMs: the producer of the residual stream (pos_embed, proj and
 # fc2 GEMM epilogues) writes x as fp32 + split-bf16 and accumulates the row statistics, so no LayerNorm kernel runs in a block
-FUSED_BLOCK_LN = os.environ.get("PSAM_FUSED_BLOCK_LN", "1") != "0"
+FUSED_BLOCK_LN = os.environ.get("PSAM_FUSED_BLOCK_LN", "1") != "0"  # capability: pack the LayerNorm-folded weights as well
+# When the LayerNorm-free form of the ViT blocks is USED (both weight sets are packed):
+#   "auto"   - only inside PipelinedPredictor captures with >= 8 clouds in flight.  MEASURED (c2): at depth 8 the folded form
+#              ties with the LayerNorm kernels (642 vs 645 clouds/s) at 49 fewer launches per cloud; at depth 4 it loses
+#              (543 vs 574) and single-stream latency is 4.0 vs 3.4 ms, because the fold needs split_k = 1 on proj / fc2.
+#   "always" / "never" - forced (tests, experiments; PSAM_BLOCK_LN_POLICY).
+BLOCK_LN_POLICY = os.environ.get("PSAM_BLOCK_LN_POLICY", "auto")
+_fold_ctx = threading.local()
+
+
+@contextlib.contextmanager
+def block_ln_fold(active: bool):
+    """Scope inside which policy "auto" resolves to `active` (set by the pipelined predictor while it captures its graphs)."""
+    prev = getattr(_fold_ctx, "active", False)
+    _fold_ctx.active = bool(active)
+    try:
+        yield
+    finally:
+        _fold_ctx.active = prev
+
+
+def _use_block_ln_fold() -> bool:
+    if BLOCK_LN_POLICY == "always":
+        return True
+    if BLOCK_LN_POLICY == "never":
+        return False
+    return bool(getattr(_fold_ctx, "active", False))
 PASSES = 3  # split-bf16 (fp32-parity) mode; 1 = plain bf16 (fails the 1e-3 parity bound, see DESIGN.md)
 
 
@@ -550,7 +576,7 @@ def run_pc_encoder(enc, coords, features):
     ops.gemm(embs, pk.wpp, bias=pk.bpp, out_f32=x, passes=PASSES)
     pos = Split(M, pk.wpos0.shape[0], dev)
     ops.small_in_linear(patches["centers"], pk.wpos0, pk.bpos0, None, None, 0.0, False, ACT_GELU, pos)
-    if pk.fold_block:
+    if pk.fold_block and _use_block_ln_fold():
         # LayerNorm-free encoder: every GEMM that writes the residual stream also writes its split-bf16 copy and row
         # statistics; norm1 / norm2 / fc_norm are applied inside the consuming GEMMs' epilogues
         nb = len(pk.blocks)

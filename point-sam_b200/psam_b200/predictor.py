@@ -196,6 +196,7 @@ class PipelinedPredictor:
         import os
 
         self.throughput_tiles = os.environ.get("PSAM_THROUGHPUT_TILES", "1") != "0"
+        self.ln_fold = depth >= 8 and self.throughput_tiles  # LayerNorm-free ViT blocks in the captured graphs (engine.BLOCK_LN_POLICY)
 
     def warmup(self, xyz, feats, pc, pl):
         from . import ops
@@ -204,8 +205,10 @@ class PipelinedPredictor:
         if self.depth > 1 and self.throughput_tiles:
             ops.GEMM_TILE_HINT = 1  # baked into the captured graphs
         try:
-            for lane in self.lanes:
-                lane.warmup(xyz, feats, pc, pl)
+            # LayerNorm-free ViT blocks only when enough clouds are in flight to hide the 16-CTA proj / fc2 launches they need
+            with engine.block_ln_fold(self.ln_fold):
+                for lane in self.lanes:
+                    lane.warmup(xyz, feats, pc, pl)
         finally:
             ops.GEMM_TILE_HINT = prev
 

@@ -38,6 +38,7 @@ def test_golden_end_to_end(golden_dir, name, fold_ln, fold_block, monkeypatch):
 
     monkeypatch.setattr(engine, "FUSED_INNER_LN", fold_ln)  # SwiGLU.norm folded into the GEMM epilogues / separate kernel
     monkeypatch.setattr(engine, "FUSED_BLOCK_LN", fold_block)  # norm1 / norm2 / fc_norm folded (LayerNorm-free blocks) / kernels
+    monkeypatch.setattr(engine, "BLOCK_LN_POLICY", "always" if fold_block else "never")
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     B, N, G, K, P, seed = [int(v) for v in g["meta"]]
     model, oracle = _build(str(g["encoder"]), G, K, 1234 + seed)
@@ -427,9 +428,14 @@ def test_iterative_graph_predictor_matches_eager_forward():
     pred(*clouds[0])  # flags were reset: a valid cloud passes again
 
 
-def test_config2_full_size_vs_fp32_oracle_on_gpu():
+@pytest.mark.parametrize("ln_policy", ["never", "always"])
+def test_config2_full_size_vs_fp32_oracle_on_gpu(ln_policy, monkeypatch):
     """BASELINE config[1] at full size (N=32768, group_number=512, group_size=64, EVA02-L, 24 blocks): the CUDA path
-    against the fp32 PyTorch oracle evaluated on the same GPU (cuBLAS fp32, TF32 off), same weights and inputs."""
+    against the fp32 PyTorch oracle evaluated on the same GPU (cuBLAS fp32, TF32 off), same weights and inputs - with the
+    LayerNorm kernels (what an eager call runs) and with the LayerNorm-free blocks (what the 8-deep pipelined predictor captures)."""
+    from psam_b200 import engine
+
+    monkeypatch.setattr(engine, "BLOCK_LN_POLICY", ln_policy)
     d = torch.device("cuda:0")
     enc, G, K, N = "eva02_large_patch14_448", 512, 64, 32768
     model, oracle = _build(enc, G, K, 21)
@@ -481,9 +487,13 @@ def test_config4_full_size_vs_fp32_oracle_on_gpu():
     _full_size_parity("eva02_large_patch14_448", 2048, 256, 131072, "kitti", 41, True)
 
 
-def test_config5_full_size_vs_fp32_oracle_on_gpu():
+@pytest.mark.parametrize("ln_policy", ["never", "always"])
+def test_config5_full_size_vs_fp32_oracle_on_gpu(ln_policy, monkeypatch):
     """BASELINE config[4] model at full size: EVA-giant (40 blocks, 16 heads x 88, fused qkv with q/v bias, GELU MLP 6144),
-    N=32768, group_number=512, group_size=64."""
+    N=32768, group_number=512, group_size=64; LayerNorm kernels and LayerNorm-free blocks (GELU MLP variant of the fold)."""
+    from psam_b200 import engine
+
+    monkeypatch.setattr(engine, "BLOCK_LN_POLICY", ln_policy)
     _full_size_parity("eva_giant_patch14_560", 512, 64, 32768, "ball", 43, False)
 
 
