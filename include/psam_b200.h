@@ -148,6 +148,7 @@ typedef struct {
     int variant;            /* 0 = policy default.  Experiment switches (the library reads no environment variable):
                              * 0x1 cta_group::2 pairs, 0x2 BK=32 4-stage ring, 0x4 scalar epilogue, 0x8 the dual-resident
                              * wide-tile kernel (two 97 KB CTAs per SM; 0x10 overrides it),
+                             * 0x80 two MMA-issuing warps for wide one-shot tiles (measured no gain: opt-in),
                              * 0x20 force / 0x40 forbid the persistent kernel (tile loop inside the CTA, double-buffered TMEM
                              * accumulator; default when the launch has >= 2 tiles per SM), bits 16-19 tiles per CTA to aim for,
                              * bits 8-11 W-tile multicast cluster size (2|4), bits 12-15 L2 prefetch depth in k-blocks */

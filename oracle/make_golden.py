@@ -133,6 +133,7 @@ def sampler_fixture(ref, out_dir):
 
 
 VORONOI = dict(B=2, N=3000, G=96, hidden=64, out=96, seed=7)      # PatchEmbedNN(7, hidden, out, G)
+HIER = dict(B=2, N=2000, G=(128, 32), K=(32, 16), radius=(0.2, 0.4), out=96, seed=9)  # PatchEmbedHier(6, out, G, K, radius)
 GROUPER_OPTS = dict(B=2, N=1500, G=40, K=24, radius=0.3, seed=8)   # KNNGrouper(use_fps=False, centralize_features=True)
 
 
@@ -153,6 +154,15 @@ def variant_fixture(ref, out_dir):
         want = oracle(xyz, feats)
         for k in ("features", "centers", "nn_idx", "embeddings"):
             assert torch.allclose(patches[k].double(), want[k].double(), atol=1e-6), k
+        h = HIER
+        xyz3, feats3 = synth.make_batch(h["B"], h["N"], h["seed"], "ball")
+        torch.manual_seed(4322)
+        oracle_h = torch_ref.PatchEmbedHier(6, h["out"], list(h["G"]), list(h["K"]), list(h["radius"])).eval()
+        model_h = ref["enc"].PatchEmbedHier(6, h["out"], list(h["G"]), list(h["K"]), list(h["radius"])).eval()
+        model_h.load_state_dict(oracle_h.state_dict(), strict=True)
+        p1, p2 = model_h(xyz3, feats3)
+        w1, w2 = oracle_h(xyz3, feats3)
+        assert torch.allclose(p1["embeddings"], w1["embeddings"], atol=1e-5) and torch.allclose(p2["embeddings"], w2["embeddings"], atol=1e-5)
         g = GROUPER_OPTS
         xyz2, feats2 = synth.make_batch(g["B"], g["N"], g["seed"], "ball")
         grp = ref["common"].KNNGrouper(g["G"], g["K"], radius=g["radius"], centralize_features=True)
@@ -164,6 +174,9 @@ def variant_fixture(ref, out_dir):
             voronoi_xyz=xyz.numpy(), voronoi_feats=feats.numpy(), voronoi_features=patches["features"].numpy(),
             voronoi_centers=patches["centers"].numpy(), voronoi_nn_idx=patches["nn_idx"].numpy().astype(np.int32),
             voronoi_embeddings=patches["embeddings"].numpy(),
+            hier_weights_checksum=state_checksum(model_h.state_dict()), hier_xyz=xyz3.numpy(), hier_feats=feats3.numpy(),
+            hier_centers1=p1["centers"].numpy(), hier_centers2=p2["centers"].numpy(), hier_emb1=p1["embeddings"].numpy(),
+            hier_emb2=p2["embeddings"].numpy(), hier_knn2_sorted=torch.sort(p2["knn_idx"], -1).values.numpy().astype(np.int32),
             grouper_meta=np.array([g["B"], g["N"], g["G"], g["K"], g["seed"]]), grouper_radius=g["radius"],
             grouper_xyz=xyz2.numpy(), grouper_feats=feats2.numpy(), grouper_features_sorted=_sorted_groups(out2).numpy(),
             grouper_centers=out2["centers"].numpy(), grouper_fps_idx=out2["fps_idx"].numpy().astype(np.int32),

@@ -247,6 +247,26 @@ class PatchEmbedNN(nn.Module):
         return patches
 
 
+class PatchEmbedHier(nn.Module):
+    """pc_sam/model/pc_encoder.py:200-239."""
+
+    def __init__(self, in_channels, out_channels, num_patches, patch_size, radius=None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.grouper1 = KNNGrouper(num_patches[0], patch_size[0], radius=radius[0] if radius else None)
+        self.patch_encoder1 = PatchEncoder(in_channels, 128, [64, 128])
+        self.grouper2 = KNNGrouper(num_patches[1], patch_size[1], radius=radius[1] if radius else None)
+        self.patch_encoder2 = PatchEncoder(128 + 3, out_channels, [128, 256])
+
+    def forward(self, coords, features):
+        patches1 = self.grouper1(coords, features)
+        x1 = self.patch_encoder1(patches1["features"])
+        patches1["embeddings"] = x1
+        patches2 = self.grouper2(patches1["centers"], x1, use_fps=False)
+        patches2["embeddings"] = self.patch_encoder2(patches2["features"])
+        return [patches1, patches2]
+
+
 # --------------------------------------------------------------------------------------------
 # timm EVA / EVA02 blocks (restated; rope=None, no CLS/abs-pos on the Point-SAM path)
 # --------------------------------------------------------------------------------------------

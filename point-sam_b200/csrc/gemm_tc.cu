@@ -35,7 +35,8 @@ constexpr int GEMM_EPI_PER_QUARTER = 4;                         // default: 16 e
 constexpr int gemm_threads(int epq) { return 64 + 128 * epq; }  // TMA warp, MMA warp, 4*epq epilogue warps
 constexpr int GEMM_THREADS = gemm_threads(GEMM_EPI_PER_QUARTER);
 // psam_gemm_out.variant bits (experiment / policy switches; no environment variable is read inside the library)
-constexpr int GV_2CTA = 0x1, GV_BK32 = 0x2, GV_SCALAR_EPI = 0x4, GV_DUAL = 0x8, GV_NO_DUAL = 0x10, GV_PERSIST = 0x20, GV_NO_PERSIST = 0x40;
+constexpr int GV_2CTA = 0x1, GV_BK32 = 0x2, GV_SCALAR_EPI = 0x4, GV_DUAL = 0x8, GV_NO_DUAL = 0x10, GV_PERSIST = 0x20, GV_NO_PERSIST = 0x40,
+              GV_TWO_ISSUERS = 0x80;
 
 struct GemmEpilogue {
     float* out_f32;            // may be null
@@ -326,7 +327,7 @@ __device__ __forceinline__ void epi_chunk_v4_dispatch(float* stg, const uint32_t
 __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const GemmEpilogue& ep, unsigned char* smem_aligned,
                                               uint32_t tmem_base, uint32_t tmem_full_bar_addr, int warp, int lane, int m_tile,
                                               int n_tile, int b1, int b2, int split, int num_kb, int BN,
-                                              int epq = GEMM_EPI_PER_QUARTER, uint32_t full_parity = 0u) {
+                                              int epq = GEMM_EPI_PER_QUARTER, uint32_t full_parity = 0u, int first_warp = 2) {
         const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
         const int row0 = m_tile * GEMM_BM + quarter * 32;
         if (num_kb > 0) {
@@ -335,8 +336,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmShape& shape, const Gemm
         }
         // One-shot kernels: all TMA loads have landed and all MMAs have retired, the pipeline stages are free to reuse
         // (smem_aligned = stage memory).  Persistent kernel: smem_aligned points at a dedicated staging area.
-        float* stg = reinterpret_cast<float*>(smem_aligned) + (warp - 2) * (32 * EPI_PITCH);  // 16-byte aligned rows
-        const int ehalf = (warp - 2) >> 2;  // the warps of a lane quarter take interleaved 32-column chunks
+        float* stg = reinterpret_cast<float*>(smem_aligned) + (warp - first_warp) * (32 * EPI_PITCH);  // 16-byte aligned rows
+        const int ehalf = (warp - first_warp) >> 2;  // the warps of a lane quarter take interleaved 32-column chunks
         const long long obase = (long long)b1 * ep.out_b1 + (long long)b2 * ep.out_b2;
         float* out = ep.out_f32 ? ep.out_f32 + obase : nullptr;
         const float* res = (ep.resid && !ep.accumulate) ? ep.resid + obase : nullptr;
@@ -585,6 +586,148 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Two-issuer variant of the one-shot wide-tile kernel (experiment, opt-in: GV_TWO_ISSUERS; see the dispatch for the measurement).
+// One thread issues a tcgen05.mma every ~120 clk at best and a 128 x 256 x 16 MMA (128 clk of tensor time) every 171 clk from
+// shared-memory operands; two issuing threads reach 150.6 clk (tools/mma_issue_probe.cu, also when both accumulate into the
+// SAME tensor-memory accumulator).  So the 12 MMAs of a 64-deep k-block are split between two warps (k-steps 0-1 / 2-3 of
+// each split-bf16 pass).  All MMAs accumulate (the epilogue warps zero the accumulator while the TMA pipeline fills), so no
+// order between the two issuers is required; the fp32 summation order of a k-block is therefore not fixed (like split-K).
+//   warp 0: TMA producer, warps 1-2: MMA issuers, warp 3: idle, warps 4-15: epilogue (three per TMEM lane quarter).
+// ---------------------------------------------------------------------------------------------
+constexpr int DUO_EPQ = 3;
+constexpr int DUO_THREADS = 128 + 128 * DUO_EPQ;
+
+template <int MAXBN, int STAGES>
+__global__ void __launch_bounds__(DUO_THREADS, 1)
+gemm_tc_duo_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmShape shape,
+                   const GemmEpilogue ep) {
+    pdl_launch_dependents();
+    constexpr int BK = 64;
+    using S = GemmSmem<MAXBN, STAGES, BK>;
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar, acc_zero_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* smem_aligned = smem_dyn + (smem_base - smem_u32(smem_dyn));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int z = blockIdx.z;
+    const int split = z % shape.split_k;
+    const int bz = z / shape.split_k;
+    const int b1 = bz % shape.nb1, b2 = bz / shape.nb1;
+    const int BN = shape.bn;
+    const int kb_total = (shape.K + BK - 1) / BK;
+    const int kb_per = (kb_total + shape.split_k - 1) / shape.split_k;
+    const int kb_begin = split * kb_per;
+    const int num_kb = max(0, min(kb_total, kb_begin + kb_per) - kb_begin);
+    const bool lo_pass = shape.passes == 3;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 2);   // both issuers release a stage
+        }
+        mbar_init(smem_u32(&tmem_full_bar), 2);      // both issuers complete the accumulator
+        mbar_init(smem_u32(&acc_zero_bar), 4 * DUO_EPQ);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), S::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane < 2) {
+            const uint32_t stage_bytes = (lo_pass ? 2u : 1u) * (uint32_t)(S::A_TILE + BN * BK * 2);
+            for (int i = 0; i < num_kb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                const uint32_t fb = smem_u32(&full_bar[s]);
+                const uint32_t sa = smem_base + s * S::STAGE;
+                const int k0 = (kb_begin + i) * BK;
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(fb, stage_bytes);
+                    tma_load_5d(sa, &tmap_a, fb, k0, m_tile * GEMM_BM, 0, b1, b2);
+                } else {
+                    tma_load_5d(sa + 2 * S::A_TILE, &tmap_b, fb, k0, n_tile * BN, 0, b1, b2);
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 2) {
+        // ===================== MMA issuers: k-steps {0,1} (warp 1) / {2,3} (warp 2) of every pass =====================
+        const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+        const int k_first = (warp - 1) * 2;
+        if (num_kb > 0) {
+            mbar_wait(smem_u32(&acc_zero_bar), 0);  // the accumulator has been zeroed
+            tc_fence_after();
+        }
+        for (int i = 0; i < num_kb; ++i) {
+            const int s = i % STAGES;
+            const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+            mbar_wait(smem_u32(&full_bar[s]), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_base + s * S::STAGE;
+                const uint64_t a_hi = umma_desc_k<BK>(sa), a_lo = umma_desc_k<BK>(sa + S::A_TILE);
+                const uint64_t b_hi = umma_desc_k<BK>(sa + 2 * S::A_TILE), b_lo = umma_desc_k<BK>(sa + 2 * S::A_TILE + BN * BK * 2);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) umma_bf16(tmem_base, a_hi + 2 * (k_first + k), b_hi + 2 * (k_first + k), idesc, 1u);
+                if (lo_pass) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) umma_bf16(tmem_base, a_lo + 2 * (k_first + k), b_hi + 2 * (k_first + k), idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) umma_bf16(tmem_base, a_hi + 2 * (k_first + k), b_lo + 2 * (k_first + k), idesc, 1u);
+                }
+                umma_commit(smem_u32(&empty_bar[s]));
+                if (i == num_kb - 1) umma_commit(smem_u32(&tmem_full_bar));
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue warps: zero the accumulator, later drain it =====================
+        if (num_kb > 0) {
+            const uint32_t q = (uint32_t)((warp & 3) * 32) << 16;
+            uint32_t zr[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t) zr[t] = 0u;
+            for (int c = (warp - 4) >> 2; c < BN / 32; c += DUO_EPQ) tmem_st_32x32(tmem_base + q + (uint32_t)(c * 32), zr);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_zero_bar));
+        }
+        gemm_epilogue(shape, ep, smem_aligned, tmem_base, smem_u32(&tmem_full_bar), warp, lane, m_tile, n_tile, b1, b2, split, num_kb, BN,
+                      DUO_EPQ, 0u, 4);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, S::TMEM_COLS);
+    }
+}
+
+template <int MAXBN, int STAGES>
+static int launch_gemm_duo(const CUtensorMap& ma, const CUtensorMap& mb, const GemmShape& sh, const GemmEpilogue& ep, cudaStream_t stream) {
+    auto kern = gemm_tc_duo_kernel<MAXBN, STAGES>;
+    using S = GemmSmem<MAXBN, STAGES, 64>;
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    const dim3 grid((unsigned)ceil_div(sh.N, sh.bn), (unsigned)ceil_div(sh.M, GEMM_BM), (unsigned)(sh.nb1 * sh.nb2 * sh.split_k));
+    PSAM_CUDA_TRY(psam::launch(kern, grid, dim3(DUO_THREADS), (size_t)S::TOTAL, stream, ma, mb, sh, ep));
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Persistent variant: grid = min(tiles, SMs); every CTA walks the linear tile index (m fastest, so the CTAs running at the
@@ -1175,5 +1318,10 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     if (bn <= 64) return launch_gemm<64, 4>(ma, mb, mbmc, sh, ep, stream);
     if (bn <= 128) return launch_gemm<128, 3>(ma, mb, mbmc, sh, ep, stream);
     if (bn <= 160) return launch_gemm<160, 3>(ma, mb, mbmc, sh, ep, stream);
+    // GV_TWO_ISSUERS: two MMA-issuing warps per wide one-shot tile.  MEASURED round 2: the issue-rate probe promised 171 -> 151
+    // clk per 128 x 256 x 16 MMA, but the kernel gains nothing in isolation (qkv 1256 vs 1266, fc1 1197 vs 1238 TFLOP/s at 8 streams)
+    // and loses in the step (616 vs 672 clouds/s, twelve epilogue warps instead of sixteen): the two-stage main loop is bound by
+    // operand latency, not by issue.  Opt-in.
+    if (cm == 1 && (variant & GV_TWO_ISSUERS) && sh.prefetch == 0) return launch_gemm_duo<256, 2>(ma, mb, sh, ep, stream);
     return launch_gemm<256, 2>(ma, mb, mbmc, sh, ep, stream);
 }

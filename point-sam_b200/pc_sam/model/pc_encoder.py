@@ -60,6 +60,22 @@ class PatchEmbedNN(nn.Module):
         return engine.run_patch_embed_nn(self, coords, features)
 
 
+class PatchEmbedHier(nn.Module):
+    """PointNet++-style tokenizer with hierarchical grouping (pc_encoder.py:200-239)."""
+
+    def __init__(self, in_channels, out_channels, num_patches, patch_size, radius=None):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.grouper1 = KNNGrouper(num_patches[0], patch_size[0], radius=radius[0] if radius else None)
+        self.patch_encoder1 = PatchEncoder(in_channels, 128, [64, 128])
+        self.grouper2 = KNNGrouper(num_patches[1], patch_size[1], radius=radius[1] if radius else None)
+        self.patch_encoder2 = PatchEncoder(128 + 3, out_channels, [128, 256])
+
+    def forward(self, coords: torch.Tensor, features: torch.Tensor):
+        return engine.run_patch_embed_hier(self, coords, features)
+
+
 class PointCloudEncoder(nn.Module):
     def __init__(self, patch_embed: PatchEmbed, transformer, embed_dim: int, patch_drop_rate=0.0):
         super().__init__()

@@ -100,6 +100,7 @@ class _PackedPatchEncoder:
         self.h1 = c2[0].out_features
         self.cout = c2[3].out_features
         self.w10, self.b10 = _f32(c1[0].weight), _f32(c1[0].bias)
+        self.w10s = ops.pack_weight(c1[0].weight) if c1[0].in_features > 16 else None
         self.g11, self.be11, self.eps11 = _f32(c1[1].weight), _f32(c1[1].bias), c1[1].eps
         self.w13, self.b13 = ops.pack_weight(c1[3].weight), _f32(c1[3].bias)
         w20 = c2[0].weight.detach().float()
@@ -117,7 +118,15 @@ def run_patch_encoder(m, patches: torch.Tensor, want_split: bool = False):
     dev = patches.device
     R, BG = B * L * K, B * L
     h1 = Split(R, pk.h0, dev)
-    ops.small_in_linear(patches, pk.w10, pk.b10, pk.g11, pk.be11, pk.eps11, True, ACT_GELU, h1)
+    if Cin <= 16 and pk.h0 % 32 == 0 and pk.h0 <= 512:
+        ops.small_in_linear(patches, pk.w10, pk.b10, pk.g11, pk.be11, pk.eps11, True, ACT_GELU, h1)
+    else:
+        # wide inputs (second level of PatchEmbedHier: 128 + 3 channels): conv1[0] on the tensor cores, LayerNorm + GELU after it
+        ps = Split(R, Cin, dev)
+        ops.split_f32(patches.reshape(R, Cin), ps)
+        u = torch.empty((R, pk.h0), dtype=torch.float32, device=dev)
+        ops.gemm(ps, pk.w10s, bias=pk.b10, out_f32=u, passes=PASSES)
+        ops.layernorm(u, pk.g11, pk.be11, pk.eps11, act=ACT_GELU, out_split=h1)
     x1s = Split(R, pk.h0, dev)
     y1s = Split(BG, pk.h0, dev)
     fused_max = K % 32 == 0  # the max-pool over the K rows of a group runs inside the GEMM epilogue
@@ -222,6 +231,17 @@ def _run_res_blocks(blocks, x: torch.Tensor):
         un = Split(rows, pb.hid, dev)
         ops.layernorm(u, pb.g1, pb.b1, pb.eps1, out_split=un)
         ops.gemm(un, pb.w2, bias=pb.bb2, out_f32=x, resid=x, passes=PASSES)
+
+
+def run_patch_embed_hier(m, coords, features):
+    """PatchEmbedHier.forward (pc_encoder.py:200-239): PointNet++-style two-level tokenizer; the second level groups the
+    first level's centres (already in FPS order: use_fps=False) with the first level's embeddings as features."""
+    patches1 = run_knn_grouper(m.grouper1, coords, features)
+    x1 = run_patch_encoder(m.patch_encoder1, patches1["features"])
+    patches1["embeddings"] = x1
+    patches2 = run_knn_grouper(m.grouper2, patches1["centers"], x1, use_fps=False)
+    patches2["embeddings"] = run_patch_encoder(m.patch_encoder2, patches2["features"])
+    return [patches1, patches2]
 
 
 def run_patch_embed_nn(m, coords, features):

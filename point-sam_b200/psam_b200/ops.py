@@ -159,7 +159,7 @@ def border_prompt(coords: torch.Tensor, gt_masks: torch.Tensor, pred_logits: Opt
 GEMM_TILE_HINT = 0  # 0 = latency-optimal tiles, 1 = SM-time-optimal tiles (set by PipelinedPredictor)
 GEMM_TILE_BN = 0    # 32..256: explicit tile width (experiments / tests)
 # psam_gemm_out.variant (experiment switches, see include/psam_b200.h); PSAM_GEMM_VARIANT seeds it once at import
-GV_2CTA, GV_BK32, GV_SCALAR_EPI, GV_DUAL, GV_NO_DUAL, GV_PERSIST, GV_NO_PERSIST = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
+GV_2CTA, GV_BK32, GV_SCALAR_EPI, GV_DUAL, GV_NO_DUAL, GV_PERSIST, GV_NO_PERSIST, GV_TWO_ISSUERS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40, 0x80
 GEMM_VARIANT = int(__import__("os").environ.get("PSAM_GEMM_VARIANT", "0"), 0)
 
 

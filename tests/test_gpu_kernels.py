@@ -564,7 +564,7 @@ def test_fused_attention_tc_reference_maximum_moves(L, step, gain):
 
 @pytest.mark.parametrize("variant", ["bn256_bk32", "bn256_bk64", "two_cta", "cluster4", "dual_resident", "throughput_policy",
                                      "persistent_bn256", "persistent_bn128", "persistent_bn64", "persistent_3_tiles_per_cta",
-                                     "never_persistent"])
+                                     "never_persistent", "two_issuers"])
 def test_gemm_tc_variants(variant, monkeypatch):
     """Opt-in / policy-selected GEMM variants (psam_gemm_out.variant / tile_hint; the library reads no environment):
     wide tiles with 64-byte-swizzled half-depth stages, the same with 128-byte swizzle, the 2-CTA cta_group::2 kernel,
@@ -577,7 +577,9 @@ def test_gemm_tc_variants(variant, monkeypatch):
                      # with several tiles per CTA forced, and switched off (the one-shot kernels on the many-row shape)
                      "persistent_bn256": (256, ops.GV_PERSIST, 0), "persistent_bn128": (128, ops.GV_PERSIST, 0),
                      "persistent_bn64": (64, ops.GV_PERSIST, 0), "persistent_3_tiles_per_cta": (0, ops.GV_PERSIST | (3 << 16), 1),
-                     "never_persistent": (0, ops.GV_NO_PERSIST, 1)}[variant]
+                     "never_persistent": (0, ops.GV_NO_PERSIST, 1),
+                     # two MMA-issuing warps accumulating into one zero-initialised TMEM accumulator (opt-in experiment)
+                     "two_issuers": (256, ops.GV_TWO_ISSUERS | ops.GV_NO_PERSIST, 0)}[variant]
     monkeypatch.setattr(ops, "GEMM_TILE_BN", bn)
     monkeypatch.setattr(ops, "GEMM_VARIANT", var)
     monkeypatch.setattr(ops, "GEMM_TILE_HINT", hint)

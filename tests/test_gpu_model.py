@@ -527,6 +527,24 @@ def test_voronoi_tokenizer_and_grouper_options_vs_reference_fixture(golden_dir):
     np.testing.assert_allclose(grp["features"].cpu().numpy(), z["voronoi_features"], atol=2e-6)
     np.testing.assert_allclose(again.cpu().numpy(), z["voronoi_features"], atol=2e-6)
     np.testing.assert_allclose(out["embeddings"].cpu().numpy(), z["voronoi_embeddings"], atol=2e-4, rtol=1e-4)
+    # hierarchical tokenizer (PatchEmbedHier, pc_encoder.py:200-239): two KNNGrouper levels, the second on FPS-ordered centres
+    from oracle.make_golden import HIER
+    from pc_sam.model.pc_encoder import PatchEmbedHier
+
+    h = HIER
+    torch.manual_seed(4322)
+    oh = torch_ref.PatchEmbedHier(6, h["out"], list(h["G"]), list(h["K"]), list(h["radius"])).eval()
+    assert state_checksum(oh.state_dict()) == str(z["hier_weights_checksum"])
+    mh = PatchEmbedHier(6, h["out"], list(h["G"]), list(h["K"]), list(h["radius"]))
+    mh.load_state_dict(oh.state_dict(), strict=True)
+    mh = mh.to(d).eval()
+    with torch.no_grad():
+        p1, p2 = mh(torch.from_numpy(z["hier_xyz"]).to(d), torch.from_numpy(z["hier_feats"]).to(d))
+    np.testing.assert_allclose(p1["centers"].cpu().numpy(), z["hier_centers1"], atol=0)
+    np.testing.assert_allclose(p2["centers"].cpu().numpy(), z["hier_centers2"], atol=0)
+    assert np.array_equal(torch.sort(p2["knn_idx"], -1).values.cpu().numpy(), z["hier_knn2_sorted"])
+    np.testing.assert_allclose(p1["embeddings"].cpu().numpy(), z["hier_emb1"], atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(p2["embeddings"].cpu().numpy(), z["hier_emb2"], atol=2e-4, rtol=1e-4)
     # KNNGrouper on FPS-ordered input with centralised features
     g = GROUPER_OPTS
     k = KNNGrouper(g["G"], g["K"], radius=g["radius"], centralize_features=True)

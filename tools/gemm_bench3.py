@@ -65,7 +65,7 @@ def bench(name, M, N, K, variant, hint, sk=1, concurrent=1, swiglu=False, reps=3
     return tf
 
 
-VARIANTS = [("oneshot", ops.GV_NO_DUAL | ops.GV_NO_PERSIST), ("dual", ops.GV_DUAL | ops.GV_NO_PERSIST), ("2cta", ops.GV_2CTA | ops.GV_NO_PERSIST),
+VARIANTS = [("oneshot", ops.GV_NO_DUAL | ops.GV_NO_PERSIST), ("oneshot2i", ops.GV_NO_DUAL | ops.GV_NO_PERSIST | ops.GV_TWO_ISSUERS), ("dual", ops.GV_DUAL | ops.GV_NO_PERSIST), ("2cta", ops.GV_2CTA | ops.GV_NO_PERSIST),
             ("persist", ops.GV_PERSIST)]
 quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
 pe_only = len(sys.argv) > 1 and sys.argv[1] == "pe"

@@ -7,6 +7,7 @@
 //   mode 4: TS + the tcgen05.ld stream
 //   mode 5/6/7: ONE issuing thread cycling over 2 / 4 / 3 disjoint accumulators (SS)   - is the floor a per-accumulator
 //   mode 8: ONE issuing thread cycling over 2 disjoint accumulators, A from TMEM (TS)    dependency or a per-thread issue cost?
+//   mode 9: SS, TWO issuing threads accumulating into the SAME accumulator (k-steps split between them)
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/mma_issue_probe.bin tools/mma_issue_probe.cu
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -39,10 +40,10 @@ __global__ void __launch_bounds__(192, 1) probe(int mode, int N, int iters, R* o
     const uint32_t tm = tmem_slot;
     const uint32_t idesc = umma_idesc_bf16(128, N);
     const uint64_t adesc = umma_desc_k_sw128(base), bdesc = umma_desc_k_sw128(base + 16384);
-    const bool two = mode == 2;
+    const bool two = mode == 2 || mode == 9;
     long long t0 = clock64();
     if ((warp == 0 || (two && warp == 1)) && lane == 0) {
-        const uint32_t d = tm + (warp == 1 ? 256u : 0u);
+        const uint32_t d = tm + ((warp == 1 && mode != 9) ? 256u : 0u);
         const int n = two ? iters / 2 : iters;
         const int chains = mode == 5 || mode == 8 ? 2 : (mode == 6 ? 4 : (mode == 7 ? 3 : 1));
         if (chains > 1) {
@@ -84,11 +85,12 @@ int main() {
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + 32768 + 1024);
     const int iters = 4096;
     const char* names[] = {"SS one issuer", "TS (A in TMEM) one issuer", "SS two issuers", "SS + tcgen05.ld stream", "TS + tcgen05.ld stream",
-                           "SS one issuer, 2 accum", "SS one issuer, 4 accum", "SS one issuer, 3 accum", "TS one issuer, 2 accum"};
+                           "SS one issuer, 2 accum", "SS one issuer, 4 accum", "SS one issuer, 3 accum", "TS one issuer, 2 accum",
+                           "SS two issuers, SAME accum"};
     printf("mode | N | clocks per MMA | ideal (128 N / 256)\n");
-    for (int mode = 0; mode < 9; ++mode)
+    for (int mode = 0; mode < 10; ++mode)
         for (int N = 64; N <= 256; N *= 2) {
-            if (mode >= 5 && N == 256) continue;  // 4 x 128 columns at most (and column 384+ holds the TS operand)
+            if (mode >= 5 && mode <= 8 && N == 256) continue;  // 4 x 128 columns at most (and column 384+ holds the TS operand)
             if (mode == 6 && N == 128) continue;
             probe<<<1, 192, 16384 + 32768 + 1024>>>(mode, N, iters, d);
             probe<<<1, 192, 16384 + 32768 + 1024>>>(mode, N, iters, d);
