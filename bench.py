@@ -559,11 +559,9 @@ def main():
     def step_e2e(i):
         for c in range(cps):
             t = pp.count
-            pp.wait_lane_free(t)  # the previous result of this lane has landed in its pinned buffers
-            if t >= pp.depth:
-                lane_i = t % pp.depth
-                pp.lanes[lane_i].raise_if_flagged()
-                chk[0] += float(pp.host_out[lane_i][1][0, 0])  # ... and the host reads it
+            if t >= pp.slots:  # the result that occupies this ticket's slot (ticket t - slots) has landed: the host reads it
+                _, iou_h = pp.result(t - pp.slots, to_host=True)
+                chk[0] += float(iou_h[0, 0])
             pp.submit(*host[(i * cps + c) % n_rot], to_host=True)
 
     timed(step_e2e, args.warmup)

@@ -80,8 +80,9 @@ class GraphPredictor:
         self.pc.copy_(pc, non_blocking=True)
         self.pl.copy_(pl, non_blocking=True)
 
-    def __call__(self, xyz, feats, pc, pl):
-        """Enqueue one step on the predictor's stream; returns device tensors (valid after ``check()`` / a stream sync)."""
+    def __call__(self, xyz, feats, pc, pl, flag_out=None):
+        """Enqueue one step on the predictor's stream; returns device tensors (valid after ``check()`` / a stream sync).
+        flag_out: pinned int32[1] that receives this step's range flag instead of the lane's own host word."""
         caller = torch.cuda.current_stream(self.dev)
         with torch.no_grad(), torch.cuda.stream(self.stream):
             self._load(xyz, feats, pc, pl, caller)
@@ -90,7 +91,7 @@ class GraphPredictor:
             else:
                 self.masks, self.iou = self._run()
             # the flag travels with the result (4 bytes) and is cleared on-stream for the lane's next step
-            self.flag_host.copy_(self.flag, non_blocking=True)
+            (flag_out if flag_out is not None else self.flag_host).copy_(self.flag, non_blocking=True)
             self.flag.zero_()
         return self.masks, self.iou
 
@@ -190,6 +191,7 @@ class PipelinedPredictor:
     def __init__(self, model, B: int, N: int, P: int, depth: int = 3, multimask_output: bool = True, use_graph: bool = True):
         self.lanes = [GraphPredictor(model, B, N, P, multimask_output, use_graph) for _ in range(depth)]
         self.depth = depth
+        self.slots = depth
         self.events = [torch.cuda.Event() for _ in range(depth)]
         self.count = 0
         self.host_out = None
@@ -217,35 +219,52 @@ class PipelinedPredictor:
         return self.lanes[0].launches_per_step
 
     def enable_host_results(self, C: int):
-        """Pinned host buffers for the D2H of (mask logits, iou) per lane."""
+        """Pinned host buffers for the D2H of (mask logits, iou).  TWO result slots per lane: the host may submit a lane's next
+        cloud before it has consumed the previous result, so a lane never idles while the host wakes up and launches (the
+        end-to-end rate used to trail the device-resident rate by ~4 %)."""
         B, N = self.lanes[0].xyz.shape[:2]
+        self.slots = 2 * self.depth
         self.host_out = [(torch.empty((B, C, N), dtype=torch.float32).pin_memory(),
-                          torch.empty((B, C), dtype=torch.float32).pin_memory()) for _ in range(self.depth)]
+                          torch.empty((B, C), dtype=torch.float32).pin_memory()) for _ in range(self.slots)]
+        self.host_flags = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(self.slots)]
+        self.events = [torch.cuda.Event() for _ in range(self.slots)]
 
     def submit(self, xyz, feats, pc, pl, to_host: bool = False) -> int:
+        """Ticket t runs on lane t % depth; its host result (to_host) lands in slot t % slots."""
         i = self.count % self.depth
+        k = self.count % self.slots
         lane = self.lanes[i]
-        masks, iou = lane(xyz, feats, pc, pl)
+        masks, iou = lane(xyz, feats, pc, pl, flag_out=self.host_flags[k] if self.host_out is not None else None)
         with torch.cuda.stream(lane.stream):
             if to_host:
-                self.host_out[i][0].copy_(masks, non_blocking=True)
-                self.host_out[i][1].copy_(iou, non_blocking=True)
-            self.events[i].record()
+                self.host_out[k][0].copy_(masks, non_blocking=True)
+                self.host_out[k][1].copy_(iou, non_blocking=True)
+            self.events[k].record()
         self.count += 1
         return self.count - 1
 
+    def _raise_if_flagged(self, ticket: int):
+        if self.host_out is None:
+            return self.lanes[ticket % self.depth].raise_if_flagged()
+        f = self.host_flags[ticket % self.slots]
+        if int(f[0]) != 0:
+            f[0] = 0
+            raise ValueError("Input coordinates must be normalized to [-1, 1].")
+
     def result(self, ticket: int, to_host: bool = False):
         """Wait for that cloud only; raises ValueError for THIS ticket if its coordinates / prompts were outside [-1, 1]
-        (the reference raises inside PositionEmbeddingRandom.forward, prompt_encoder.py:44-46)."""
+        (the reference raises inside PositionEmbeddingRandom.forward, prompt_encoder.py:44-46).  Device results (to_host
+        False) are valid until the lane's next submit; host results until `slots` further submits."""
+        self.events[ticket % self.slots].synchronize()
+        self._raise_if_flagged(ticket)
         i = ticket % self.depth
-        self.events[i].synchronize()
-        self.lanes[i].raise_if_flagged()
-        return self.host_out[i] if to_host else (self.lanes[i].masks, self.lanes[i].iou)
+        return self.host_out[ticket % self.slots] if to_host else (self.lanes[i].masks, self.lanes[i].iou)
 
     def wait_lane_free(self, ticket: int):
-        """Block until the lane that `ticket` will use has finished its previous cloud (host buffers reusable)."""
-        if ticket >= self.depth:
-            self.events[ticket % self.depth].synchronize()
+        """Block until the result slot that `ticket` will use has been produced by its previous owner (ticket - slots): after
+        this returns the host may read that result and then reuse the slot."""
+        if ticket >= self.slots:
+            self.events[ticket % self.slots].synchronize()
 
     def synchronize(self):
         for lane in self.lanes:

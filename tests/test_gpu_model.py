@@ -200,12 +200,12 @@ def test_graph_and_pipelined_predictors_match_eager():
     tickets = []
     for (xyz, feats), (pc, pl) in zip(clouds, prompts):
         pp.wait_lane_free(pp.count)
-        if pp.count >= pp.depth:  # the host consumes the lane's previous result before the lane is reused
-            t_old = pp.count - pp.depth
+        if pp.count >= pp.slots:  # the host consumes the slot's previous result before the slot is reused
+            t_old = pp.count - pp.slots
             m, i = pp.result(t_old, to_host=True)
             torch.testing.assert_close(m, want[t_old][0], atol=2e-5, rtol=1e-4)
         tickets.append(pp.submit(xyz.pin_memory(), feats.pin_memory(), pc.pin_memory(), pl.pin_memory(), to_host=True))
-    for t in tickets[-pp.depth:]:
+    for t in tickets[-pp.slots:]:
         m, i = pp.result(t, to_host=True)
         torch.testing.assert_close(m, want[t][0], atol=2e-5, rtol=1e-4)
         torch.testing.assert_close(i, want[t][1], atol=2e-5, rtol=1e-4)
