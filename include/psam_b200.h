@@ -161,6 +161,15 @@ typedef struct {
 int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, const psam_gemm_out* out, int passes, int split_k,
                      cudaStream_t stream);
 
+/* Row-complete GEMM with LayerNorm and activation in the epilogue:
+ *   Y = act(LayerNorm(A W^T + gbias[row / group_rows])) as split-bf16, A [M,K<=128], W [N,K] with N = 256 or 512 (a CTA owns
+ * 128 rows x the full width, so the row statistics stay on the SM and the fp32 pre-activation never reaches memory).
+ * Replaces conv2[0..2] of PatchEncoder (Linear on cat[max, x] = W_a max + W_b x, LayerNorm, GELU; common.py:491-495):
+ * gbias carries W_a max + b per group.  gamma / beta [N]; out_hi [M, ldo_s] hi plane, lo plane out_plane elements further. */
+int psam_gemm_rowln_bf16x3(const psam_operand* a, const psam_operand* w, const float* gbias, long long ld_gbias, int group_rows,
+                           const float* gamma, const float* beta, float eps, int act, void* out_hi, long long out_plane,
+                           long long ldo_s, int passes, cudaStream_t stream);
+
 /* Fused encoder self-attention on tensor cores: out = softmax(Q K^T * scale) V per (cloud, head).
  * q/k/v are split-bf16 operand views [L rows x dh] with nb1 = heads, nb2 = clouds (typically three column windows of
  * the fused qkv activation).  dh == 64, any L >= 1 (PSAM_ERR_UNSUPPORTED otherwise - the caller then uses

@@ -881,6 +881,215 @@ gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row-complete GEMM with LayerNorm + GELU in the epilogue (mini-PointNet conv2[0..2], pc_sam/model/common.py:491-495):
+//     Y = GELU(LayerNorm(A W^T + gbias[row / group_rows]))  ->  split-bf16
+// A CTA owns 128 rows x the FULL output width N = 256 NH (NH = 1 or 2 accumulators of 256 TMEM columns), so the row statistics
+// never leave the SM and the fp32 pre-activation (32768 x 512 floats = 64 MB per cloud, written by the GEMM and read back by
+// the LayerNorm kernel before) never reaches memory.  K <= 128: the A tile (both k-blocks, hi + lo = 64 KB) stays in shared
+// memory while W streams through one 128 KB buffer, one 256-row half at a time (W is L2-resident: every CTA reads the same 256 KB).
+// Persistent over the m-tiles.  warp 0: TMA, warp 1: MMA, warps 2-17: epilogue (four per TMEM lane quarter, N / 4 columns each):
+// pass 1 reads the accumulator once for shifted sums (Chan's parallel variance across the four parts of a row), pass 2 reads
+// it again, normalises, applies GELU and stores both bf16 planes straight from registers (64 contiguous bytes per thread).
+// ---------------------------------------------------------------------------------------------
+struct RowLnParams {
+    int M, N, K, passes;
+    const float* gbias;   // [M / group_rows, N] or null
+    long long ld_gbias;
+    int group_rows;
+    const float* gamma;   // [N]
+    const float* beta;    // [N]
+    float eps;
+    int act;
+    __nv_bfloat16* out_hi;  // [M, ldo_s] hi plane, lo plane at + out_plane
+    long long out_plane, ldo_s;
+};
+
+constexpr int RL_THREADS = 576;  // TMA warp, MMA warp, 16 epilogue warps (four threads per row, N / 4 columns each)
+constexpr int RL_A_TILE = 128 * 64 * 2;                  // one plane of one k-block of A
+constexpr int RL_W_TILE = 256 * 64 * 2;                  // one plane of one k-block of a W half
+constexpr int RL_SMEM = 2 * 2 * RL_A_TILE + 2 * 2 * RL_W_TILE + 1024;  // A: 2 k-blocks x (hi, lo); W half: 2 k-blocks x (hi, lo)
+
+__global__ void __launch_bounds__(RL_THREADS, 1)
+gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const RowLnParams p) {
+    pdl_launch_dependents();
+    extern __shared__ unsigned char smem_dyn[];
+    __shared__ __align__(8) uint64_t a_full, a_empty, w_full, w_empty, acc_full, acc_empty;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float2 s_part[2][4][128];  // [tile parity][part][row]: (mean, M2) of each quarter of a row
+
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    const uint32_t sA = smem_base, sW = smem_base + 4 * RL_A_TILE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int MT = ceil_div(p.M, GEMM_BM);
+    const int NH = p.N / 256;                      // accumulators (halves of the row)
+    const int KB = ceil_div(p.K, 64);              // k-blocks (1 or 2)
+    const bool lo_pass = p.passes == 3;
+    const uint32_t planes = lo_pass ? 2u : 1u;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+        mbar_init(smem_u32(&a_full), 1);
+        mbar_init(smem_u32(&a_empty), 1);
+        mbar_init(smem_u32(&w_full), 1);
+        mbar_init(smem_u32(&w_empty), 1);
+        mbar_init(smem_u32(&acc_full), 1);
+        mbar_init(smem_u32(&acc_empty), 16);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0, wit = 0;
+            for (int tile = blockIdx.x; tile < MT; tile += gridDim.x, ++it) {
+                mbar_wait(smem_u32(&a_empty), (it & 1u) ^ 1u);
+                mbar_arrive_expect_tx(smem_u32(&a_full), planes * (uint32_t)(KB * RL_A_TILE));
+                for (int kb = 0; kb < KB; ++kb)  // one 3-D box per k-block: 64 x 128 rows x {hi, lo}
+                    tma_load_5d(sA + kb * 2 * RL_A_TILE, &tmap_a, smem_u32(&a_full), kb * 64, tile * GEMM_BM, 0, 0, 0);
+                for (int h = 0; h < NH; ++h, ++wit) {
+                    mbar_wait(smem_u32(&w_empty), (wit & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(smem_u32(&w_full), planes * (uint32_t)(KB * RL_W_TILE));
+                    for (int kb = 0; kb < KB; ++kb)
+                        tma_load_5d(sW + kb * 2 * RL_W_TILE, &tmap_w, smem_u32(&w_full), kb * 64, h * 256, 0, 0, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = umma_idesc_bf16(GEMM_BM, 256);
+        uint32_t it = 0, wit = 0;
+        for (int tile = blockIdx.x; tile < MT; tile += gridDim.x, ++it) {
+            mbar_wait(smem_u32(&acc_empty), (it & 1u) ^ 1u);  // the epilogue has drained the accumulators of the previous tile
+            mbar_wait(smem_u32(&a_full), it & 1u);
+            tc_fence_after();
+            for (int h = 0; h < NH; ++h, ++wit) {
+                mbar_wait(smem_u32(&w_full), wit & 1u);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t d = tmem_base + (uint32_t)(h * 256);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        const uint32_t sa = sA + kb * 2 * RL_A_TILE, sw = sW + kb * 2 * RL_W_TILE;
+                        const uint64_t a_hi = umma_desc_k_sw128(sa), a_lo = umma_desc_k_sw128(sa + RL_A_TILE);
+                        const uint64_t b_hi = umma_desc_k_sw128(sw), b_lo = umma_desc_k_sw128(sw + RL_W_TILE);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(d, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        if (lo_pass) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_bf16(d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_bf16(d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                        }
+                    }
+                    umma_commit(smem_u32(&w_empty));                       // this W half may be overwritten
+                    if (h == NH - 1) {
+                        umma_commit(smem_u32(&a_empty));                   // the A tile too
+                        umma_commit(smem_u32(&acc_full));
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== epilogue: thread = (row, quarter of the row's columns) =====================
+        const int quarter = warp & 3, part = (warp - 2) >> 2;  // four warps per TMEM lane quarter, one per column part
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        const int cols_part = p.N / 4;                           // 64 or 128 columns per thread
+        const int col_base = part * cols_part;                   // first global column of this thread
+        const int c_count = cols_part / 32;                      // 32-column chunks
+        const uint32_t t_acc = tmem_base + lane_off + (uint32_t)col_base;  // accumulator h occupies TMEM columns [256 h, 256 h + 256)
+        const float inv_n = 1.0f / (float)p.N;
+        const float n_part = (float)cols_part;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < MT; tile += gridDim.x, ++it) {
+            const int row = tile * GEMM_BM + r;
+            const bool row_ok = row < p.M;
+            const float* gb = (p.gbias && row_ok) ? p.gbias + (long long)(row / p.group_rows) * p.ld_gbias : nullptr;
+            mbar_wait(smem_u32(&acc_full), it & 1u);
+            tc_fence_after();
+            // ---- pass 1: shifted sums of this thread's half of the row ----
+            float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < c_count; ++c) {
+                uint32_t v[32];
+                const int col0 = col_base + c * 32;
+                tmem_ld_32x32(t_acc + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+                if (c == 0) shift = __uint_as_float(v[0]) + (gb ? gb[col0] : 0.f);
+#pragma unroll
+                for (int t = 0; t < 32; t += 4) {
+                    const float4 g4 = gb ? *reinterpret_cast<const float4*>(gb + col0 + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float x0 = __uint_as_float(v[t]) + g4.x - shift, x1 = __uint_as_float(v[t + 1]) + g4.y - shift,
+                                x2 = __uint_as_float(v[t + 2]) + g4.z - shift, x3 = __uint_as_float(v[t + 3]) + g4.w - shift;
+                    s1 += (x0 + x1) + (x2 + x3);
+                    s2 = fmaf(x0, x0, fmaf(x1, x1, fmaf(x2, x2, fmaf(x3, x3, s2))));
+                }
+            }
+            const float mean_h = shift + s1 / n_part;
+            const float m2_h = fmaxf(s2 - s1 * s1 / n_part, 0.f);
+            s_part[it & 1u][part][r] = make_float2(mean_h, m2_h);
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + quarter) : "memory");  // the four warps of this lane quarter
+            const float2 o0 = s_part[it & 1u][0][r], o1 = s_part[it & 1u][1][r], o2 = s_part[it & 1u][2][r], o3 = s_part[it & 1u][3][r];
+            const float mean = 0.25f * ((o0.x + o1.x) + (o2.x + o3.x));
+            // equal part sizes: M2 = sum M2_p + n_p sum (mean_p - mean)^2   (Chan et al., pairwise combination)
+            const float d0 = o0.x - mean, d1 = o1.x - mean, d2 = o2.x - mean, d3 = o3.x - mean;
+            const float var = (((o0.y + o1.y) + (o2.y + o3.y)) + n_part * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3))) * inv_n;
+            const float rstd = rsqrtf(var + p.eps);
+            // ---- pass 2: normalise, activate, store both planes ----
+            __nv_bfloat16* ohi = p.out_hi + (long long)row * p.ldo_s;
+            __nv_bfloat16* olo = ohi + p.out_plane;
+#pragma unroll 1
+            for (int c = 0; c < c_count; ++c) {
+                uint32_t v[32];
+                const int col0 = col_base + c * 32;
+                tmem_ld_32x32(t_acc + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+                uint32_t hh[16], ll[16];
+#pragma unroll
+                for (int t = 0; t < 32; t += 4) {
+                    const float4 g4 = gb ? *reinterpret_cast<const float4*>(gb + col0 + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 ga = *reinterpret_cast<const float4*>(p.gamma + col0 + t);
+                    const float4 be = *reinterpret_cast<const float4*>(p.beta + col0 + t);
+                    const float y0 = apply_act(fmaf((__uint_as_float(v[t]) + g4.x - mean) * rstd, ga.x, be.x), p.act);
+                    const float y1 = apply_act(fmaf((__uint_as_float(v[t + 1]) + g4.y - mean) * rstd, ga.y, be.y), p.act);
+                    const float y2 = apply_act(fmaf((__uint_as_float(v[t + 2]) + g4.z - mean) * rstd, ga.z, be.z), p.act);
+                    const float y3 = apply_act(fmaf((__uint_as_float(v[t + 3]) + g4.w - mean) * rstd, ga.w, be.w), p.act);
+                    __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+                    split_bf16(y0, h0, l0);
+                    split_bf16(y1, h1, l1);
+                    split_bf16(y2, h2, l2);
+                    split_bf16(y3, h3, l3);
+                    hh[t >> 1] = pack_bf16x2(h0, h1), hh[(t >> 1) + 1] = pack_bf16x2(h2, h3);
+                    ll[t >> 1] = pack_bf16x2(l0, l1), ll[(t >> 1) + 1] = pack_bf16x2(l2, l3);
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        *reinterpret_cast<uint4*>(ohi + col0 + q4 * 8) = make_uint4(hh[q4 * 4], hh[q4 * 4 + 1], hh[q4 * 4 + 2], hh[q4 * 4 + 3]);
+                        *reinterpret_cast<uint4*>(olo + col0 + q4 * 8) = make_uint4(ll[q4 * 4], ll[q4 * 4 + 1], ll[q4 * 4 + 2], ll[q4 * 4 + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&acc_empty));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 2-CTA variant (tcgen05 cta_group::2): two CTAs of a cluster (consecutive m-tiles) act as one 256 x BN MMA.
 // Each CTA streams its own 128 A rows and only HALF of the W tile (BN/2 rows); the tensor cores of the pair read
 // both halves, so the operand bytes ingested per SM and flop drop by 1/3 (BN=256: 64 KB instead of 96 KB per
@@ -1324,4 +1533,36 @@ extern "C" int psam_gemm_bf16x3(const psam_operand* a, const psam_operand* w, co
     // operand latency, not by issue.  Opt-in.
     if (cm == 1 && (variant & GV_TWO_ISSUERS) && sh.prefetch == 0) return launch_gemm_duo<256, 2>(ma, mb, sh, ep, stream);
     return launch_gemm<256, 2>(ma, mb, mbmc, sh, ep, stream);
+}
+
+extern "C" int psam_gemm_rowln_bf16x3(const psam_operand* a, const psam_operand* w, const float* gbias, long long ld_gbias, int group_rows,
+                                      const float* gamma, const float* beta, float eps, int act, void* out_hi, long long out_plane,
+                                      long long ldo_s, int passes, cudaStream_t stream) {
+    using namespace psam;
+    if (!a || !w || !a->hi || !w->hi || !gamma || !beta || !out_hi) return PSAM_ERR_ARG;
+    if (a->k != w->k || a->rows <= 0 || (passes != 1 && passes != 3)) return PSAM_ERR_ARG;
+    if ((w->rows != 256 && w->rows != 512) || a->k <= 0 || a->k > 128) return PSAM_ERR_UNSUPPORTED;
+    if ((a->nb1 > 1) || (a->nb2 > 1) || (w->nb1 > 1) || (w->nb2 > 1)) return PSAM_ERR_UNSUPPORTED;
+    if (gbias && (group_rows <= 0 || (ld_gbias & 3) || (reinterpret_cast<uintptr_t>(gbias) & 15))) return PSAM_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(out_hi)) & 15) return PSAM_ERR_ARG;
+    if ((ldo_s & 7) || (out_plane & 7) || ldo_s < w->rows) return PSAM_ERR_ARG;
+    RowLnParams p;
+    p.M = a->rows, p.N = w->rows, p.K = a->k, p.passes = passes;
+    p.gbias = gbias, p.ld_gbias = ld_gbias, p.group_rows = group_rows > 0 ? group_rows : 1;
+    p.gamma = gamma, p.beta = beta, p.eps = eps, p.act = act;
+    p.out_hi = (__nv_bfloat16*)out_hi, p.out_plane = out_plane, p.ldo_s = ldo_s;
+    CUtensorMap ma, mw;
+    int rc = make_operand_map(&ma, a, GEMM_BM, passes == 3 ? 2 : 1);
+    if (rc) return rc;
+    rc = make_operand_map(&mw, w, 256, passes == 3 ? 2 : 1);
+    if (rc) return rc;
+    int nsm = 148, devid = 0;
+    if (cudaGetDevice(&devid) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, devid);
+    const int mt = ceil_div(p.M, GEMM_BM);
+    const int per = ceil_div(mt, nsm);
+    const int ctas = ceil_div(mt, per);
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(gemm_rowln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_SMEM));
+    PSAM_CUDA_TRY(psam::launch(gemm_rowln_kernel, dim3((unsigned)ctas), dim3(RL_THREADS), (size_t)RL_SMEM, stream, ma, mw, p));
+    PSAM_LAUNCH_CHECK();
+    return PSAM_OK;
 }

@@ -30,6 +30,7 @@ FUSED_MASK_DOT = os.environ.get("PSAM_FUSED_MASK_DOT", "1") != "0"
 DECODER_TC = os.environ.get("PSAM_DECODER_TC", "1") != "0"
 # norm1 / norm2 / fc_norm folded into the qkv / fc1 / out_proj GEMMs: the producer of the residual stream (pos_embed, proj and
 # fc2 GEMM epilogues) writes x as fp32 + split-bf16 and accumulates the row statistics, so no LayerNorm kernel runs in a block
+FUSED_ROW_LN = os.environ.get("PSAM_FUSED_ROW_LN", "1") != "0"  # mini-PointNet conv2[0] + LayerNorm + GELU in one row-complete GEMM
 FUSED_BLOCK_LN = os.environ.get("PSAM_FUSED_BLOCK_LN", "1") != "0"  # capability: pack the LayerNorm-folded weights as well
 # When the LayerNorm-free form of the ViT blocks is USED (both weight sets are packed):
 #   "auto"   - only inside PipelinedPredictor captures with >= 8 clouds in flight.  MEASURED (c2): at depth 8 the folded form
@@ -141,10 +142,15 @@ def run_patch_encoder(m, patches: torch.Tensor, want_split: bool = False):
     # conv2[0] on cat([max, x]) = W_a max + W_b x + b : the pooled half is computed once per group
     t = torch.empty((BG, pk.h1), dtype=torch.float32, device=dev)
     ops.gemm(y1s, pk.w20a, bias=pk.b20, out_f32=t, passes=PASSES)
-    x2 = torch.empty((R, pk.h1), dtype=torch.float32, device=dev)
-    ops.gemm(x1s, pk.w20b, out_f32=x2, passes=PASSES)
     h2 = Split(R, pk.h1, dev)
-    ops.layernorm(x2, pk.g21, pk.be21, pk.eps21, gbias=t, group_rows=K, act=ACT_GELU, out_split=h2)
+    if FUSED_ROW_LN and ops.gemm_rowln_supported(pk.h0, pk.h1):
+        # conv2[0] on the per-point half + group bias + LayerNorm + GELU in ONE kernel: a CTA owns the full row, the fp32
+        # pre-activation (R x h1 floats: 64 MB per cloud at c2) never reaches memory
+        ops.gemm_rowln(x1s, pk.w20b, pk.g21, pk.be21, pk.eps21, h2, gbias=t, group_rows=K, act=ACT_GELU, passes=PASSES)
+    else:
+        x2 = torch.empty((R, pk.h1), dtype=torch.float32, device=dev)
+        ops.gemm(x1s, pk.w20b, out_f32=x2, passes=PASSES)
+        ops.layernorm(x2, pk.g21, pk.be21, pk.eps21, gbias=t, group_rows=K, act=ACT_GELU, out_split=h2)
     embs = Split(BG, pk.cout, dev) if want_split else None
     if fused_max:
         emb = torch.full((B, L, pk.cout), float("-inf"), dtype=torch.float32, device=dev)

@@ -202,6 +202,19 @@ def gemm(a: Split, w: Split, *, bias=None, out_f32: Optional[torch.Tensor] = Non
     gemm_raw(a.operand(rows=M), w.operand(), o, passes, split_k)
 
 
+def gemm_rowln(a: Split, w: Split, gamma, beta, eps: float, out: Split, *, gbias: Optional[torch.Tensor] = None, group_rows: int = 0,
+               act: int = ACT_NONE, passes: int = 3):
+    """out = act(LayerNorm(a @ w^T + gbias[row // group_rows])) as split-bf16; K <= 128, N in {256, 512} (psam_gemm_rowln_bf16x3)."""
+    ao, wo = a.operand(), w.operand()
+    nv.check(nv.lib().psam_gemm_rowln_bf16x3(byref(ao), byref(wo), nv.ptr(gbias), gbias.shape[-1] if gbias is not None else 0, group_rows,
+                                             nv.ptr(gamma), nv.ptr(beta), float(eps), act, out.ptr(), out.plane, out.pitch, passes,
+                                             nv.stream()), "gemm_rowln_bf16x3")
+
+
+def gemm_rowln_supported(K: int, N: int) -> bool:
+    return K <= 128 and N in (256, 512)
+
+
 def linear_f32(x, w, b=None, *, x2=None, r=None, act=ACT_NONE, out=None, M=None, K=None, ldx=None, Z=1, x_z=0, x2_z=0,
                w_z=0, b_z=0, r_z=0, y_z=0, ldy=None, x_off=0):
     """fp32 SIMT linear (see psam_linear_f32). x [.., K] flattened to rows unless M/ldx given."""

@@ -599,3 +599,27 @@ def test_gemm_tc_variants(variant, monkeypatch):
             assert float((osp.float() - out).abs().max()) < 3e-5 * max(1.0, float(want.abs().max()))
         err = float((out - want.float()).abs().max())
         assert err < 5e-5 * max(1.0, float(want.abs().max())), (variant, M, N, K, err)
+
+
+@pytest.mark.parametrize("M,N,K,group_rows", [(32768, 512, 128, 64), (1000, 512, 128, 8), (640, 256, 64, 32), (300, 512, 100, 0),
+                                              (128 * 149 * 2 + 5, 256, 128, 1)])
+def test_gemm_rowln_fused_layernorm_gelu(M, N, K, group_rows):
+    """psam_gemm_rowln_bf16x3: GELU(LayerNorm(A W^T + group bias)) with the full output row inside one CTA (mini-PointNet
+    conv2[0..2]) against fp64, including a mean much larger than the spread (the shifted sums must not cancel), ragged last
+    tiles, K tails and more tiles than SMs."""
+    ops = _ops()
+    a, w = _rand(M, K, seed=71), _rand(N, K, seed=72, scale=K ** -0.5)
+    gamma, beta = 1.0 + 0.1 * _rand(N, seed=73), 0.1 * _rand(N, seed=74)
+    gb = None
+    if group_rows:
+        gb = _rand((M + group_rows - 1) // group_rows, N, seed=75) + 30.0  # |mean| >> std
+    A, W = ops.pack_weight(a), ops.pack_weight(w)
+    out = ops.Split(M, N, _dev())
+    out.t.fill_(float("nan"))
+    ops.gemm_rowln(A, W, gamma, beta, 1e-5, out, gbias=gb, group_rows=group_rows, act=1)
+    x = a.double() @ w.double().t()
+    if gb is not None:
+        x = x + gb.double().repeat_interleave(group_rows, 0)[:M]
+    want = torch.nn.functional.gelu(torch.nn.functional.layer_norm(x, (N,), gamma.double(), beta.double(), 1e-5))
+    err = float((out.float().double() - want).abs().max())
+    assert err < 3e-4 if group_rows else err < 5e-5, (M, N, K, err)

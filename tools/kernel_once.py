@@ -1,5 +1,5 @@
 """Launch one hot kernel in isolation between cudaProfilerStart/Stop (for `ncu --profile-from-start off --set full`).
-usage: python tools/kernel_once.py {attention_long|attention|knn|knn_c4|border|gemm_qkv|gemm_qkv_single|gemm_fc1|gemm_m2048|gemm_pe|fps}"""
+usage: python tools/kernel_once.py {attention_long|attention|knn|knn_c4|border|gemm_qkv|gemm_qkv_single|gemm_fc1|gemm_m2048|gemm_pe|gemm_rowln|fps}"""
 import os
 import sys
 from ctypes import byref
@@ -53,6 +53,16 @@ def gemm(M, N, K, hint, variant=0):
     return lambda: ops.gemm(a, w, out_f32=out, passes=3)
 
 
+def gemm_rowln(M=32768, N=512, K=128, group_rows=64):
+    a, w = ops.Split(M, K, dev), ops.Split(N, K, dev)
+    a.t.normal_()
+    w.t.normal_()
+    gb = torch.randn(M // group_rows, N, device=dev)
+    gamma, beta = torch.ones(N, device=dev), torch.zeros(N, device=dev)
+    out = ops.Split(M, N, dev)
+    return lambda: ops.gemm_rowln(a, w, gamma, beta, 1e-5, out, gbias=gb, group_rows=group_rows, act=1)
+
+
 def fps(N, G=512):
     xyz, _ = synth.make_batch(1, N, 5, "ball")
     x = xyz.to(dev)
@@ -63,7 +73,7 @@ fn = {"attention_long": lambda: attention(2048), "attention": lambda: attention(
       "knn_c4": lambda: knn(131072, 2048, 256, "kitti"), "border": lambda: border(32768), "gemm_qkv": lambda: gemm(512, 3072, 1024, 1),
       "gemm_pe": lambda: gemm(32768, 512, 128, 1),
       "gemm_qkv_single": lambda: gemm(512, 3072, 1024, 1, ops.GV_NO_DUAL), "gemm_fc1": lambda: gemm(512, 5504, 1024, 1),
-      "gemm_m2048": lambda: gemm(2048, 3072, 1024, 1), "fps": lambda: fps(32768)}[what]()
+      "gemm_m2048": lambda: gemm(2048, 3072, 1024, 1), "gemm_rowln": lambda: gemm_rowln(), "fps": lambda: fps(32768)}[what]()
 for _ in range(3):
     fn()
 torch.cuda.synchronize()

@@ -5,8 +5,8 @@ O=gpurun_out
 mkdir -p $O
 echo "== tests"; timeout 2400 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 | tee $O/r2_gpu_tests.log
 grep -q " failed\| error" $O/r2_gpu_tests.log && exit 1
-bash tools/r2_step_ncu.sh attention gemm_qkv gemm_m2048 gemm_pe fps knn
-rm -f $O/r2_gemm_qkv.source.csv $O/r2_gemm_m2048.source.csv $O/r2_gemm_pe.source.csv
+bash tools/r2_step_ncu.sh attention gemm_qkv gemm_m2048 gemm_pe gemm_rowln fps knn
+rm -f $O/r2_gemm_qkv.source.csv $O/r2_gemm_m2048.source.csv $O/r2_gemm_pe.source.csv $O/r2_gemm_rowln.source.csv
 bash tools/r2_step_launches.sh
 python tools/ncu_traffic.py $O/r2_launches_c2.csv $O/r2_gemm_traffic.json
 echo "== tokenizer sweep"; timeout 300 python tools/tokenizer_sweep.py 2>&1 | tee $O/r2_tokenizer_sweep.md | tail -12
