@@ -16,7 +16,7 @@ namespace psam {
 
 constexpr int KNN_THREADS = 256;
 constexpr int KNN_MAX_CAP = 16384;     // candidate list capacity limit
-constexpr int KNN_MAX_SAMPLE = 16384;  // sample distances kept in shared memory
+constexpr int KNN_MAX_SAMPLE = 16384;  // sample size limit (bounds the cost of phase A)
 
 __device__ __forceinline__ float sqdist3(float x, float y, float z, float cx, float cy, float cz) {
     const float dx = x - cx, dy = y - cy, dz = z - cz;
@@ -100,16 +100,12 @@ __device__ uint32_t kth_smallest_radix(const float* vals, int n, int k, int* his
 // the upper edge of the bin that holds the k-th element.  At most 12.5 % above the k-th value - good enough for the
 // candidate filter of phase A (a looser tau only admits a few more candidates), at a third of the passes and barriers of
 // the exact select.
-__device__ uint32_t kth_upper_bound_hist(const float* vals, int n, int k, int* hist) {
+__device__ uint32_t kth_upper_bound_from_hist(const int* hist, int k) {
     __shared__ int s_warp_tot2[KNN_THREADS / 32];
     __shared__ int s_digit2;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nb = 2048, per = nb / KNN_THREADS;
-    __syncthreads();
-    for (int i = tid; i < nb; i += KNN_THREADS) hist[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += KNN_THREADS) atomicAdd(&hist[__float_as_uint(vals[i]) >> 20], 1);
-    __syncthreads();
+    __syncthreads();  // histogram complete; previous use of the static slots finished
     int local = 0;
 #pragma unroll
     for (int t = 0; t < per; ++t) local += hist[tid * per + t];
@@ -166,11 +162,11 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ key, int Q
            int sample_cap, int cap, long long* __restrict__ idx_out, float* __restrict__ d2_out) {
     pdl_prologue();
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_sample = reinterpret_cast<float*>(smem_raw);       // [C][sample_cap]
-    float* c_d2_all = s_sample + (size_t)C * sample_cap;        // [C][cap]
+    float* s_sample = reinterpret_cast<float*>(smem_raw);       // [sample_cap = 2K]: the final list of the centre being finished
+    float* c_d2_all = s_sample + sample_cap;                    // [C][cap]
     int* c_idx_all = reinterpret_cast<int*>(c_d2_all + (size_t)C * cap);  // [C][cap]
     int* cnt = c_idx_all + (size_t)C * cap;                     // [64]
-    int* hist = cnt + 64;                                       // [KNN_HIST]
+    int* hist = cnt + 64;                                       // [C][KNN_HIST]: per-centre sample histograms (phase A); [0] reused by the selects
     __shared__ int s_ncand[C], s_overflow[C], s_nsel;
     __shared__ uint32_t s_tau[C];
     __shared__ int s_wcnt[KNN_THREADS / 32];
@@ -189,9 +185,11 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ key, int Q
     zero_counters(cnt);
 
     // ---- A. sample bound per centre ------------------------------------------------------------
-    // the strided sample is loaded ONCE for the C centres, eight points per thread at a time with all 24 loads in flight
-    // (the loop used to expose one L2 round trip per sample and per centre)
+    // the strided sample is loaded ONCE for the C centres, eight points per thread at a time with all 24 loads in flight; its
+    // squared distances go straight into one 2048-bin histogram per centre (top 11 bits) - the sample itself is never stored
     const int ns = (N + sample_stride - 1) / sample_stride;
+    for (int i = tid; i < C * KNN_HIST; i += KNN_THREADS) hist[i] = 0;
+    __syncthreads();
     for (int i0 = 0; i0 < ns; i0 += 8 * KNN_THREADS) {
         float sx[8], sy[8], sz[8];
 #pragma unroll
@@ -203,16 +201,15 @@ knn_kernel(const float* __restrict__ query, const float* __restrict__ key, int Q
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * KNN_THREADS + tid;
-            if (i < ns) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) s_sample[(size_t)c * sample_cap + i] = sqdist3(sx[u], sy[u], sz[u], cx[c], cy[c], cz[c]);
+            for (int c = 0; c < C; ++c) {
+                if (i < ns) atomicAdd(&hist[c * KNN_HIST + (__float_as_uint(sqdist3(sx[u], sy[u], sz[u], cx[c], cy[c], cz[c])) >> 20)], 1);
             }
         }
     }
-    __syncthreads();
 #pragma unroll 1
     for (int c = 0; c < C; ++c) {
-        const uint32_t t = kth_upper_bound_hist(s_sample + (size_t)c * sample_cap, ns, K, hist);
+        const uint32_t t = kth_upper_bound_from_hist(hist + c * KNN_HIST, K);
         if (tid == 0) s_tau[c] = t;
     }
     __syncthreads();
@@ -777,16 +774,17 @@ extern "C" int psam_knn_f32(const float* query, const float* key, int B, int Q, 
     while ((long long)K * stride * 2 <= 1024 && (N + 2 * stride - 1) / (2 * stride) >= 4 * K) stride *= 2;
     while ((N + stride - 1) / stride > KNN_MAX_SAMPLE) stride *= 2;
     const int ns = (N + stride - 1) / stride;
-    int sample_cap = ns > 2 * K ? ns : 2 * K;
-    sample_cap = (sample_cap + 3) & ~3;
-    long long cap = (long long)4 * K * stride;
+    (void)ns;
+    int sample_cap = (2 * K + 3) & ~3;  // scratch for the final (distance, index) list of one centre
+    // candidate capacity per centre: the bound admits ~1.2 K stride keys (sampling std ~ K^-1/2); beyond it the exact fallback runs
+    long long cap = (long long)2 * K * stride;
     if (cap < 1024) cap = 1024;
     if (cap > KNN_MAX_CAP) cap = KNN_MAX_CAP;
     if (cap > N) cap = (N + 3) & ~3;  // cannot hold more candidates than keys
     if (cap < K) return PSAM_ERR_UNSUPPORTED;
     // centres per CTA: as many as keep >= 1.5 CTAs per SM (the per-centre select phases are latency-bound: they need
     // co-resident CTAs to overlap) and fit two CTAs' shared memory on an SM
-    auto smem_for = [&](int c) { return (size_t)c * sample_cap * 4 + (size_t)c * cap * 8 + (64 + KNN_HIST) * 4; };
+    auto smem_for = [&](int c) { return (size_t)sample_cap * 4 + (size_t)c * cap * 8 + (64 + (size_t)c * KNN_HIST) * 4; };
     int C = 4;
     while (C > 1 && ((long long)B * ((Q + C - 1) / C) < 222 || smem_for(C) > 100 * 1024)) C /= 2;
     const size_t smem = smem_for(C);
