@@ -172,7 +172,8 @@ int psam_gemm_rowln_bf16x3(const psam_operand* a, const psam_operand* w, const f
 
 /* Fused encoder self-attention on tensor cores: out = softmax(Q K^T * scale) V per (cloud, head).
  * q/k/v are split-bf16 operand views [L rows x dh] with nb1 = heads, nb2 = clouds (typically three column windows of
- * the fused qkv activation).  dh == 64, any L >= 1 (PSAM_ERR_UNSUPPORTED otherwise - the caller then uses
+ * the fused qkv activation).  dh == 64 or 88 (EVA-giant; the 88-wide head is handled as 64 + 24 columns, zero padded by
+ * TMA), any L >= 1 (PSAM_ERR_UNSUPPORTED otherwise - the caller then uses
  * psam_gemm_bf16x3 + psam_softmax_split).  Key blocks are streamed once: S_j lands in a ring of tensor-memory slots,
  * P_j = exp2(S_j c - m_ref) is written back into the slot as split-bf16 and consumed as the TMEM A operand of the PV
  * MMA; the reference maximum is moved (and O rescaled) only when a block exceeds it by more than 2^8.

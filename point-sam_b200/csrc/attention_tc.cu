@@ -588,7 +588,7 @@ constexpr int AP_STAGES = 4;        // K / V blocks in flight (32 KB each)
 constexpr int AP_SLOTS = 2;         // S / P slots of 128 TMEM columns (with two query tiles: one per softmax group)
 constexpr float AP_TAU = 40.0f;     // log2 units
 constexpr int AP_THREADS = 352;     // warps 0-3: softmax group 0, 4-7: group 1, 8: TMA, 9: S issuer (+ TMEM allocation), 10: PV issuer
-constexpr int AP_SMEM_TOTAL = 2 * ATT_SMEM_Q + AP_STAGES * ATT_SMEM_STAGE + 1024;
+constexpr int AP_SMEM_TOTAL = 2 * ATT_SMEM_Q + AP_STAGES * ATT_SMEM_STAGE + 1024;  // dh = 64: 2 Q tiles + 4 stages; dh = 88: 1 Q tile of 2 chunks + 2 stages of 2 chunks
 
 // D[tmem] (+)= A[tmem] * B[smem desc]: P is read from tensor memory (row = lane, two bf16 per 32-bit column along K)
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -636,9 +636,21 @@ __device__ __forceinline__ float ex2f(float x) {
 __device__ __forceinline__ float bf16lo_f(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16hi_f(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
 
+// DH = 64: one 64-column chunk per Q / K / V tile, two query tiles per CTA.
+// DH = 88 (EVA-giant): two 64-column chunks, the second holds columns 64..87 and zeros (TMA fills what lies beyond the head's
+// extent); S uses 4 + 2 k-steps, the PV operand [V_hi0 | V_lo0 | V_hi1 | V_lo1] is 256 wide (four 64-column N atoms 16 KB
+// apart), O_t takes 256 TMEM columns, so a CTA holds ONE query tile and the stage ring two blocks.
+template <int DH>
 __global__ void __launch_bounds__(AP_THREADS, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                       const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+    constexpr int NCH = DH <= 64 ? 1 : 2;                 // 64-column chunks of a head
+    constexpr int KS_LAST = DH <= 64 ? 4 : (DH - 64 + 15) / 16;  // 16-wide k-steps of the last chunk that hold data
+    constexpr int Q_BYTES = NCH * ATT_SMEM_Q;             // one query tile (all chunks, hi + lo)
+    constexpr int ST_BYTES = NCH * ATT_SMEM_STAGE;        // one K or V block
+    constexpr int STAGES = DH <= 64 ? AP_STAGES : 2;
+    constexpr int NT_MAX = DH <= 64 ? 2 : 1;              // query tiles per CTA
+    constexpr int OC = 128 * NCH;                         // TMEM columns of one O_t: [P V_hi | P V_lo] per chunk
     pdl_launch_dependents();
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t q_full, pv_done[2];
@@ -648,11 +660,12 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     const uint32_t sQ = smem_base;                    // Q tile t at sQ + t * ATT_SMEM_Q (hi plane, lo plane)
-    const uint32_t sKV = sQ + 2 * ATT_SMEM_Q;
+    const uint32_t sKV = sQ + NT_MAX * Q_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.y, b = blockIdx.z;
-    const int q_tile0 = blockIdx.x * p.tiles_per_cta;                          // first of the (up to) two query tiles
-    const int nt = min(p.tiles_per_cta, (p.L + ATT_BQ - 1) / ATT_BQ - q_tile0);  // query tiles of this CTA
+    const int tpc = min(p.tiles_per_cta, NT_MAX);
+    const int q_tile0 = blockIdx.x * tpc;                                      // first of the (up to) two query tiles
+    const int nt = min(tpc, (p.L + ATT_BQ - 1) / ATT_BQ - q_tile0);            // query tiles of this CTA
     const int nkb = (p.L + ATT_BKEY - 1) / ATT_BKEY;
     const int G = nt * nkb;                                                    // items: g = j * nt + t
 
@@ -663,7 +676,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         mbar_init(smem_u32(&q_full), 1);
         mbar_init(smem_u32(&pv_done[0]), 1);
         mbar_init(smem_u32(&pv_done[1]), 1);
-        for (int s = 0; s < AP_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&kv_full[s]), 1);
             mbar_init(smem_u32(&kv_empty[s]), 1);
         }
@@ -678,7 +691,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
-    const uint32_t t_o = tmem_base;           // O_t: columns [128 t, 128 t + 128): P V_hi in the first 64, P V_lo in the last 64
+    const uint32_t t_o = tmem_base;           // O_t: columns [OC t, OC t + OC): per 64-column chunk of the head P V_hi then P V_lo
     const uint32_t t_s = tmem_base + 256u;    // slot s: columns [256 + 128 s, +128)
     pdl_wait();
     if (threadIdx.x == 0) att_trace(p, 0);  // trace layout: 0 start | 1 q_full seen | 2 + 8 g + {0 S issued, 1 PV issued, 2 s_full seen, 3 first chunk fetched, 4 exps done, 5 p_full arrive} | 200 end
@@ -693,14 +706,17 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     if (warp == 8) {
         if (lane == 0) {
             const uint32_t qb = smem_u32(&q_full);
-            mbar_arrive_expect_tx(qb, (uint32_t)(nt * ATT_SMEM_Q));
-            for (int t = 0; t < nt; ++t) tma_load_5d(sQ + t * ATT_SMEM_Q, &tmap_q, qb, 0, (q_tile0 + t) * ATT_BQ, 0, h, b);
+            mbar_arrive_expect_tx(qb, (uint32_t)(nt * Q_BYTES));
+            for (int t = 0; t < nt; ++t)
+                for (int ch = 0; ch < NCH; ++ch)  // one 3-D box per 64-column chunk: 64 x 128 rows x {hi, lo}
+                    tma_load_5d(sQ + t * Q_BYTES + ch * ATT_SMEM_Q, &tmap_q, qb, 64 * ch, (q_tile0 + t) * ATT_BQ, 0, h, b);
             for (int i = 0; i < 2 * nkb; ++i) {
-                const int s = i % AP_STAGES;
-                mbar_wait(smem_u32(&kv_empty[s]), ((uint32_t)(i / AP_STAGES) & 1u) ^ 1u);
+                const int s = i % STAGES;
+                mbar_wait(smem_u32(&kv_empty[s]), ((uint32_t)(i / STAGES) & 1u) ^ 1u);
                 const uint32_t fb = smem_u32(&kv_full[s]);
-                mbar_arrive_expect_tx(fb, ATT_SMEM_STAGE);
-                tma_load_5d(sKV + s * ATT_SMEM_STAGE, (i & 1) ? &tmap_v : &tmap_k, fb, 0, (i >> 1) * ATT_BKEY, 0, h, b);
+                mbar_arrive_expect_tx(fb, ST_BYTES);
+                for (int ch = 0; ch < NCH; ++ch)
+                    tma_load_5d(sKV + s * ST_BYTES + ch * ATT_SMEM_STAGE, (i & 1) ? &tmap_v : &tmap_k, fb, 64 * ch, (i >> 1) * ATT_BKEY, 0, h, b);
             }
         }
     } else if (warp == 9) {
@@ -711,21 +727,24 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         if (lane == 0) att_trace(p, 1);
         for (int g = 0; g < G; ++g) {
             const int t = g % nt, j = g / nt, slot = g % AP_SLOTS;
-            const int i = 2 * j, ks = i % AP_STAGES;
-            if (t == 0) mbar_wait(smem_u32(&kv_full[ks]), (uint32_t)(i / AP_STAGES) & 1u);  // first use of K_j
+            const int i = 2 * j, ks = i % STAGES;
+            if (t == 0) mbar_wait(smem_u32(&kv_full[ks]), (uint32_t)(i / STAGES) & 1u);  // first use of K_j
             if (g >= AP_SLOTS) mbar_wait(smem_u32(&pv_done[t]), (uint32_t)((g - AP_SLOTS) / nt) & 1u);  // PV_{g-2} has read the slot
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t sq = sQ + t * ATT_SMEM_Q, sk = sKV + ks * ATT_SMEM_STAGE;
-                const uint64_t q_hi = umma_desc_k_sw128(sq), q_lo = umma_desc_k_sw128(sq + ATT_TILE);
-                const uint64_t k_hi = umma_desc_k_sw128(sk), k_lo = umma_desc_k_sw128(sk + ATT_TILE);
                 const uint32_t d_s = t_s + (uint32_t)(slot * ATT_BKEY);
 #pragma unroll
-                for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_hi + 2 * k, k_hi + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                for (int pass = 0; pass < 3; ++pass) {  // Q_hi K_hi, Q_lo K_hi, Q_hi K_lo
 #pragma unroll
-                for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_lo + 2 * k, k_hi + 2 * k, idesc_s, 1u);
+                    for (int ch = 0; ch < NCH; ++ch) {
+                        const uint32_t sq = sQ + t * Q_BYTES + ch * ATT_SMEM_Q, sk = sKV + ks * ST_BYTES + ch * ATT_SMEM_STAGE;
+                        const uint64_t qd = umma_desc_k_sw128(sq + (pass == 1 ? ATT_TILE : 0));
+                        const uint64_t kd = umma_desc_k_sw128(sk + (pass == 2 ? ATT_TILE : 0));
 #pragma unroll
-                for (int k = 0; k < ATT_DH / 16; ++k) umma_bf16(d_s, q_hi + 2 * k, k_lo + 2 * k, idesc_s, 1u);
+                        for (int k = 0; k < (ch == NCH - 1 ? KS_LAST : 4); ++k)
+                            umma_bf16(d_s, qd + 2 * k, kd + 2 * k, idesc_s, (pass > 0 || ch > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
                 if (t == nt - 1) umma_commit(smem_u32(&kv_empty[ks]));  // last use of K_j
                 umma_commit(smem_u32(&s_full[slot]));
                 att_trace(p, 2 + 8 * g + 0);
@@ -734,17 +753,17 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         }
     } else if (warp == 10) {
         // ===================== PV issuer =====================
-        constexpr uint32_t idesc_o = umma_idesc_bf16(128, 2 * ATT_DH) | (1u << 16);  // B = [V_hi | V_lo] MN-major; A (P) from TMEM
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, OC) | (1u << 16);  // B = [V_hi | V_lo] per chunk, MN-major; A (P) from TMEM
         for (int g = 0; g < G; ++g) {
             const int t = g % nt, j = g / nt, slot = g % AP_SLOTS;
-            const int i = 2 * j + 1, vs = i % AP_STAGES;
-            if (t == 0) mbar_wait(smem_u32(&kv_full[vs]), (uint32_t)(i / AP_STAGES) & 1u);  // first use of V_j
+            const int i = 2 * j + 1, vs = i % STAGES;
+            if (t == 0) mbar_wait(smem_u32(&kv_full[vs]), (uint32_t)(i / STAGES) & 1u);  // first use of V_j
             mbar_wait(smem_u32(&p_full[slot]), (uint32_t)(g / AP_SLOTS) & 1u);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t sv = sKV + vs * ATT_SMEM_STAGE;
+                const uint32_t sv = sKV + vs * ST_BYTES;
                 const uint64_t v_hi = umma_desc_mn_sw128(sv);
-                const uint32_t a0 = t_s + (uint32_t)(slot * ATT_BKEY), d_o = t_o + (uint32_t)(t * 2 * ATT_DH);
+                const uint32_t a0 = t_s + (uint32_t)(slot * ATT_BKEY), d_o = t_o + (uint32_t)(t * OC);
                 // The tensor-memory A operand is read at ~64 B/clk: a 128 x 16 P step costs 64 clk whatever N is, so both P
                 // planes run against the 128-wide B operand [V_hi | V_lo] (the lo tile is the next 64-wide N atom of the MN-major
                 // descriptor, 16 KB further): two passes of N = 128 instead of three of N = 64 - a third fewer P reads and MMA
@@ -770,7 +789,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         const int quarter = warp & 3;             // TMEM lane quarter this warp may access
         const int r = quarter * 32 + lane;        // row inside the tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-        const uint32_t t_orow = t_o + lane_off + (uint32_t)(t * 2 * ATT_DH);
+        const uint32_t t_orow = t_o + lane_off + (uint32_t)(t * OC);
         const float c = p.scale_log2e;
         const float2 c2 = make_float2(c, c);
         float mref = __int_as_float(0xff800000);  // -inf: the first chunk of the row sets the reference
@@ -809,7 +828,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                         waited_pv = true;
                         tc_fence_after();
 #pragma unroll 1
-                        for (int hh = 0; hh < 4; ++hh) {
+                        for (int hh = 0; hh < OC / 32; ++hh) {
                             uint32_t o[32];
                             tmem_ld_32x32(t_orow + (uint32_t)(hh * 32), o);
                             tmem_ld_wait();
@@ -876,27 +895,30 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         __nv_bfloat16* ohi = p.out_hi + (long long)b * p.out_b + (long long)h * p.out_h + (long long)qrow * p.ldo;
         __nv_bfloat16* olo = ohi + p.out_plane;
 #pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
+        for (int hh = 0; hh < (DH + 31) / 32; ++hh) {  // 32 output columns at a time: chunk hh / 2 of the head, half hh % 2 of it
             uint32_t o[32], o2[32];
-            tmem_ld_32x32(t_orow + (uint32_t)(hh * 32), o);             // P V_hi
-            tmem_ld_32x32(t_orow + (uint32_t)(ATT_DH + hh * 32), o2);   // P V_lo
+            const uint32_t cbase = (uint32_t)((hh >> 1) * 128 + (hh & 1) * 32);
+            tmem_ld_32x32(t_orow + cbase, o);         // P V_hi
+            tmem_ld_32x32(t_orow + cbase + 64u, o2);  // P V_lo
             tmem_ld_wait();
 #pragma unroll
             for (int i2 = 0; i2 < 32; ++i2) o[i2] = __float_as_uint(__uint_as_float(o[i2]) + __uint_as_float(o2[i2]));
             if (qrow < p.L) {
 #pragma unroll
                 for (int i2 = 0; i2 < 32; i2 += 8) {
-                    uint32_t oh[4], ol[4];
+                    if (hh * 32 + i2 < DH) {  // DH = 88: the last group of 32 holds 24 columns
+                        uint32_t oh[4], ol[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        __nv_bfloat16 h0, l0, h1, l1;
-                        split_bf16(__uint_as_float(o[i2 + 2 * u]) * inv, h0, l0);
-                        split_bf16(__uint_as_float(o[i2 + 2 * u + 1]) * inv, h1, l1);
-                        oh[u] = pack_bf16x2(h0, h1);
-                        ol[u] = pack_bf16x2(l0, l1);
+                        for (int u = 0; u < 4; ++u) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            split_bf16(__uint_as_float(o[i2 + 2 * u]) * inv, h0, l0);
+                            split_bf16(__uint_as_float(o[i2 + 2 * u + 1]) * inv, h1, l1);
+                            oh[u] = pack_bf16x2(h0, h1);
+                            ol[u] = pack_bf16x2(l0, l1);
+                        }
+                        *reinterpret_cast<uint4*>(ohi + hh * 32 + i2) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                        *reinterpret_cast<uint4*>(olo + hh * 32 + i2) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
                     }
-                    *reinterpret_cast<uint4*>(ohi + hh * 32 + i2) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-                    *reinterpret_cast<uint4*>(olo + hh * 32 + i2) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
                 }
             }
         }
@@ -926,7 +948,7 @@ static int attention_setup(const psam_operand* q, const psam_operand* k, const p
     if (!q || !k || !v || !out_hi) return PSAM_ERR_ARG;
     const int L = q->rows, dh = q->k;
     const int H = q->nb1 > 0 ? q->nb1 : 1, B = q->nb2 > 0 ? q->nb2 : 1;
-    if (dh != ATT_DH || L <= 0) return PSAM_ERR_UNSUPPORTED;
+    if ((dh != 64 && dh != 88) || L <= 0) return PSAM_ERR_UNSUPPORTED;
     if (k->rows != L || v->rows != L || k->k != dh || v->k != dh) return PSAM_ERR_ARG;
     if ((ldo | out_plane | out_head_stride | out_cloud_stride) & 7) return PSAM_ERR_ARG;
     int rc = make_operand_map_ext(mq, q, ATT_BQ, 2);
@@ -959,9 +981,15 @@ extern "C" int psam_attention_bf16x3(const psam_operand* q, const psam_operand* 
     dim3 grid;
     int rc = attention_setup(q, k, v, out_hi, out_plane, ldo, out_head_stride, out_cloud_stride, scale, &mq, &mk, &mv, &p, &grid);
     if (rc) return rc;
+    if (q->k == 88) {  // EVA-giant heads: one query tile per CTA
+        PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_pair_kernel<88>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM_TOTAL));
+        PSAM_CUDA_TRY(psam::launch(attention_pair_kernel<88>, dim3(grid), dim3(AP_THREADS), (size_t)(AP_SMEM_TOTAL), stream, mq, mk, mv, p));
+        PSAM_LAUNCH_CHECK();
+        return PSAM_OK;
+    }
     grid.x = (grid.x + p.tiles_per_cta - 1) / p.tiles_per_cta;  // one or two query tiles per CTA
-    PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM_TOTAL));
-    PSAM_CUDA_TRY(psam::launch(attention_pair_kernel, dim3(grid), dim3(AP_THREADS), (size_t)(AP_SMEM_TOTAL), stream, mq, mk, mv, p));
+    PSAM_CUDA_TRY(cudaFuncSetAttribute(attention_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM_TOTAL));
+    PSAM_CUDA_TRY(psam::launch(attention_pair_kernel<64>, dim3(grid), dim3(AP_THREADS), (size_t)(AP_SMEM_TOTAL), stream, mq, mk, mv, p));
     PSAM_LAUNCH_CHECK();
     return PSAM_OK;
 }
@@ -973,6 +1001,7 @@ extern "C" int psam_attention_bf16x3_twopass(const psam_operand* q, const psam_o
     CUtensorMap mq, mk, mv;
     AttnParams p;
     dim3 grid;
+    if (q && q->k != ATT_DH) return PSAM_ERR_UNSUPPORTED;  // the first-generation kernels cover dh = 64 only
     int rc = attention_setup(q, k, v, out_hi, out_plane, ldo, out_head_stride, out_cloud_stride, scale, &mq, &mk, &mv, &p, &grid);
     if (rc) return rc;
     if (p.L > 512) {  // two-sweep kernel: S streamed through a ring of TMEM slots

@@ -506,13 +506,12 @@ def test_linear_attention_posenc_misc():
     torch.testing.assert_close(got.reshape(4, 48), want, atol=0, rtol=0)
 
 
-def _attention_case(qkv, B, H, L, entry):
+def _attention_case(qkv, B, H, L, entry, dh=64):
     from ctypes import byref
 
     from psam_b200 import native as nv
 
     ops = _ops()
-    dh = 64
     D = H * dh
     QKV = ops.Split(B * L, 3 * D, _dev())
     ops.split_f32(qkv, QKV)
@@ -534,6 +533,15 @@ def test_fused_attention_tc(B, H, L, entry):
     """psam_attention_bf16x3 (streaming kernel: S ring in TMEM, P written back into TMEM as the A operand of the PV MMA,
     lazily moved reference maximum) and the first-generation two-pass kernels vs fp64 attention."""
     got, want = _attention_case(_rand(B * L, 3 * 64 * H, seed=21), B, H, L, entry)
+    err = float((got - want).abs().max())
+    assert err < 5e-5 * max(1.0, float(want.abs().max())), err
+
+
+@pytest.mark.parametrize("B,H,L", [(1, 16, 512), (2, 3, 128), (1, 2, 200), (1, 2, 7), (1, 3, 640), (1, 2, 1100)])
+def test_fused_attention_tc_head_dim_88(B, H, L):
+    """EVA-giant heads (dh = 88) on the fused kernel: the head is loaded as 64 + 24 columns (TMA zero-fills up to 128), S uses
+    4 + 2 k-steps, the PV operand is 256 wide; vs fp64 attention."""
+    got, want = _attention_case(_rand(B * L, 3 * 88 * H, seed=23), B, H, L, "psam_attention_bf16x3", dh=88)
     err = float((got - want).abs().max())
     assert err < 5e-5 * max(1.0, float(want.abs().max())), err
 
