@@ -655,7 +655,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     extern __shared__ unsigned char smem_dyn[];
     __shared__ __align__(8) uint64_t q_full, pv_done[2];
     __shared__ __align__(8) uint64_t kv_full[AP_STAGES], kv_empty[AP_STAGES];
-    __shared__ __align__(8) uint64_t s_full[AP_SLOTS], p_full[AP_SLOTS];
+    __shared__ __align__(8) uint64_t s_full[AP_SLOTS], p_full[AP_SLOTS], slot_free[AP_SLOTS];
     __shared__ uint32_t tmem_base_smem;
 
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -683,6 +683,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         for (int s = 0; s < AP_SLOTS; ++s) {
             mbar_init(smem_u32(&s_full[s]), 1);
             mbar_init(smem_u32(&p_full[s]), 128);  // the 128 threads of one softmax group
+            mbar_init(smem_u32(&slot_free[s]), 1);
         }
         fence_mbar_init();
     }
@@ -700,7 +701,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     // N = 64 and N = 128 from one thread, half that from two), and an item needs 12 + 16 of them: a single issuing warp was
     // the bottleneck of this kernel (softmax warps idle half of the time, profiles/r02).  So TWO warps issue: warp 9 the
     // S_g = Q_t K_j^T products, warp 10 the O_t += P_g [V_hi | V_lo] products.  The only ordering between them - S_{g+2}
-    // overwrites the slot PV_g reads P from - goes through pv_done (tcgen05.commit of PV_g).
+    // overwrites the slot PV_g reads P from - goes through slot_free (tcgen05.commit of PV_g, one barrier per slot).
     // The stage ring carries K_0 V_0 K_1 V_1 ...: K_j at position 2 j (S issuer), V_j at 2 j + 1 (PV issuer); a block is
     // released after its last use (tile nt - 1).
     if (warp == 8) {
@@ -729,7 +730,11 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             const int t = g % nt, j = g / nt, slot = g % AP_SLOTS;
             const int i = 2 * j, ks = i % STAGES;
             if (t == 0) mbar_wait(smem_u32(&kv_full[ks]), (uint32_t)(i / STAGES) & 1u);  // first use of K_j
-            if (g >= AP_SLOTS) mbar_wait(smem_u32(&pv_done[t]), (uint32_t)((g - AP_SLOTS) / nt) & 1u);  // PV_{g-2} has read the slot
+            // PV_{g-2} has read the slot S_g overwrites.  One barrier per SLOT: its next completion is PV_g, which cannot happen
+            // before S_g is issued, so this parity wait can never be lapped.  (Waiting on the per-tile pv_done here deadlocked
+            // when a CTA holds a single query tile: PV_{g-1} may retire while this warp still waits for K_g, the barrier is then
+            // two phases ahead and the parity test waits for a completion that needs S_g.)
+            if (g >= AP_SLOTS) mbar_wait(smem_u32(&slot_free[slot]), (uint32_t)(g / AP_SLOTS - 1) & 1u);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t d_s = t_s + (uint32_t)(slot * ATT_BKEY);
@@ -779,6 +784,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     umma_bf16_ts(d_o, a0 + (uint32_t)(32 * (kk >> 1) + 8 * (kk & 1) + 16), v_hi + (uint64_t)(kk * (2048 >> 4)), idesc_o, 1u);
                 if (t == nt - 1) umma_commit(smem_u32(&kv_empty[vs]));  // last use of V_j
                 umma_commit(smem_u32(&pv_done[t]));
+                umma_commit(smem_u32(&slot_free[slot]));
                 att_trace(p, 2 + 8 * g + 1);
             }
             __syncwarp();
