@@ -31,9 +31,9 @@ DECODER_TC = os.environ.get("PSAM_DECODER_TC", "1") != "0"
 # norm1 / norm2 / fc_norm folded into the qkv / fc1 / out_proj GEMMs: the producer of the residual stream (pos_embed, proj and
 # fc2 GEMM epilogues) writes x as fp32 + split-bf16 and accumulates the row statistics, so no LayerNorm kernel runs in a block
 # EVA-giant heads (dh = 88) on the fused attention kernel (64 + 24 columns, zero padded by TMA).  Full-size parity of the 40-block
-# model holds with it (tests/test_gpu_model.py::test_config5_full_size_vs_fp32_oracle_on_gpu, both LayerNorm forms); its throughput
-# on c5 could not be measured any more in round 2 (GPU budget), PSAM_FUSED_ATTENTION_DH88=0 selects the unfused tensor-core path
-# (QK^T GEMM, softmax, V transpose, PV GEMM) it replaces.
+# model holds with it (tests/test_gpu_model.py::test_config5_full_size_vs_fp32_oracle_on_gpu, both LayerNorm forms); c5: 213 -> 243
+# clouds/s (profiles/r02_bench_c5_fused_dh88.json).  PSAM_FUSED_ATTENTION_DH88=0 selects the unfused tensor-core path (QK^T GEMM,
+# softmax, V transpose, PV GEMM) it replaces.
 FUSED_ATTENTION_DH88 = os.environ.get("PSAM_FUSED_ATTENTION_DH88", "1") != "0"
 FUSED_ROW_LN = os.environ.get("PSAM_FUSED_ROW_LN", "1") != "0"  # mini-PointNet conv2[0] + LayerNorm + GELU in one row-complete GEMM
 FUSED_BLOCK_LN = os.environ.get("PSAM_FUSED_BLOCK_LN", "1") != "0"  # capability: pack the LayerNorm-folded weights as well
