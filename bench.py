@@ -342,17 +342,14 @@ def only_regime(pp, keep, reps: int):
 def run_c3(name, args, model, dev, dist, rank, world, barrier):
     from pc_sam.model.loss import compute_iou
     from psam_b200 import synth
-    from psam_b200.parallel import gather_metric, shard_range
+    from psam_b200.parallel import gather_metric, plan_graph_chunks, shard_range
 
     enc, N, G, K, total, chunk, iters, M = C3[name]
     lo, hi = shard_range(total, rank, world)
     n_local = hi - lo
     # clouds per CUDA graph: at most C3's 4, fewer when the rank's shard is small, so that `c3_lanes` graphs stay in flight on
     # every rank count (8 ranks x 4 clouds: four 1-cloud graphs overlap instead of one 4-cloud graph running alone)
-    chunk = max(1, min(chunk, n_local // max(1, args.c3_lanes)))
-    while chunk > 1 and n_local % chunk:
-        chunk -= 1
-    n_chunks = n_local // max(1, chunk)
+    chunk, n_chunks = plan_graph_chunks(n_local, args.c3_lanes, chunk)
     saved = model.prompt_iters
     model.prompt_iters = iters
     n_lanes = min(n_chunks, args.c3_lanes)

@@ -29,3 +29,13 @@ def gather_metric(local: torch.Tensor, total: int) -> torch.Tensor:
     out: List[torch.Tensor] = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return torch.cat([o[: b - a] for o, (a, b) in zip(out, sizes)], dim=0)
+
+
+def plan_graph_chunks(n_local: int, lanes: int, max_chunk: int) -> Tuple[int, int]:
+    """Clouds per CUDA graph and number of graphs for a rank's shard of a fixed batch (bench.py config c3): at most
+    `max_chunk` clouds per graph, fewer when the shard is small so that `lanes` graphs stay in flight on every rank count
+    (8 ranks x 4 clouds: four 1-cloud graphs overlap instead of one 4-cloud graph running alone); the chunk divides the shard."""
+    chunk = max(1, min(max_chunk, n_local // max(1, lanes)))
+    while chunk > 1 and n_local % chunk:
+        chunk -= 1
+    return chunk, n_local // max(1, chunk)

@@ -139,3 +139,17 @@ def test_sharded_evaluation_matches_single_process(tmp_path):
         assert omean == pytest.approx(single["object_mean"].tolist(), abs=1e-6)
         for k in per:
             assert per[k] == pytest.approx(single["per_object"][k].tolist(), abs=1e-6)
+
+
+def test_c3_graph_chunk_plan_for_every_rank_count():
+    """bench.py config c3: 32 clouds over 1 / 2 / 4 / 8 ranks, four graphs in flight per rank, at most 4 clouds per graph."""
+    from psam_b200.parallel import plan_graph_chunks, shard_range
+
+    for world, want in ((1, (4, 8)), (2, (4, 4)), (4, (2, 4)), (8, (1, 4))):
+        for rank in range(world):
+            lo, hi = shard_range(32, rank, world)
+            assert plan_graph_chunks(hi - lo, 4, 4) == want, (world, rank)
+    assert plan_graph_chunks(7, 4, 4) == (1, 7)      # prime shard: single-cloud graphs
+    assert plan_graph_chunks(6, 4, 4) == (1, 6)
+    assert plan_graph_chunks(12, 2, 4) == (4, 3)
+    assert plan_graph_chunks(1, 4, 4) == (1, 1)
