@@ -39,6 +39,15 @@ def test_argument_validation_without_gpu(lib_path):
     lib.psam_fps_workspace_bytes.restype = ctypes.c_size_t
     assert lib.psam_fps_workspace_bytes(1, 32768, 512) == 0            # register-resident plan
     assert lib.psam_fps_workspace_bytes(2, 200000, 512) == 2 * 200000 * 4  # streaming plan
+    # round-2 entry points: rejected before any CUDA call as well
+    lib.psam_voronoi_features_f32.restype = ctypes.c_int
+    assert lib.psam_voronoi_features_f32(None, None, None, None, 1, 1, 8, 4, 3, None, None, 0, 0, None) == -1
+    lib.psam_scatter_amax_f32.restype = ctypes.c_int
+    assert lib.psam_scatter_amax_f32(None, None, 1, 8, 4, 6, None, None) == -1
+    lib.psam_gemm_rowln_bf16x3.restype = ctypes.c_int
+    assert lib.psam_gemm_rowln_bf16x3(None, None, None, 0, 0, None, None, ctypes.c_float(1e-5), 1, None, 0, 0, 3, None) == -1
+    lib.psam_group_gather_f32.restype = ctypes.c_int
+    assert lib.psam_group_gather_f32(None, None, None, None, None, 1, 1, 8, 4, 2, 3, ctypes.c_float(0.0), None, None) == -1
 
 
 def test_state_dict_contract_and_api_surface():
