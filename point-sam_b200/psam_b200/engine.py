@@ -722,10 +722,12 @@ def run_point_encoder(pe, points, labels, check=True):
 def run_mask_encoder(me, masks, coords, centers, knn_idx, center_idx=None):
     if masks is None:
         return me.no_mask_embed.weight.reshape(1, 1, -1).expand(centers.shape[0], centers.shape[1], -1)
-    if me.centralize_features:
-        raise NotImplementedError("centralize_features=True is not used by the released configs")
+    if me.centralize_features and center_idx is None:
+        raise RuntimeError("MaskEncoder(centralize_features=True) needs center_idx (the FPS indices of the centres)")
     m = masks.detach().float().contiguous().unsqueeze(-1)
-    groups = ops.group_gather(coords.float().contiguous(), m, centers, knn_idx, me.radius)
+    # centralize_features (prompt_encoder.py:121-130 -> common.py:181-185): one more channel, logit - logit at the group's centre
+    groups = ops.group_gather(coords.float().contiguous(), m, centers, knn_idx, me.radius,
+                              center_idx=center_idx.contiguous() if me.centralize_features else None)
     return run_patch_encoder(me.patch_encoder, groups)
 
 
